@@ -1,0 +1,1471 @@
+// pms_api.cpp — implementation of the C ABI in include/percept_smoother_c.h.
+//
+// Host-side restatement of the control flow of
+//   ReferenceMeshSmootherConjugateGradientImpl (SM/ReferenceMeshSmootherConjugateGradientDef.hpp:330-591, 906-1093, 1481-1520)
+//   ReferenceMeshSmootherBaseImpl::run_algorithm (SM/ReferenceMeshSmootherBase.cpp:216-334)
+// with every data-parallel step dispatched to the sm_100a kernels of pms_kernels.cu.  Scalars are
+// `double`, i.e. the reference's `Double` typedef under KOKKOS_ENABLE_CUDA (MeshType.hpp:41-46).
+// There is no CPU compute path in this file: all field arithmetic happens in CUDA kernels.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <numeric>
+
+#include "pms_ctx.h"
+
+using pmsk::MeshDev;
+
+static const char* FIELD_NAMES3[] = {"coordinates", "coordinates_N", "coordinates_NM1", "coordinates_lagged",
+                                     "cg_g",        "cg_r",          "cg_d",            "cg_s"};
+static const char* FIELD_NAMES1[] = {"cg_edge_length", "num_adj_elems"};
+
+DField& pms_ctx::field(const char* name) {
+  auto it = fields.find(name);
+  if (it == fields.end()) throw PmsError(PMS_ERR_ARG, std::string("unknown field '") + name + "' (did you call pms_commit?)");
+  return it->second;
+}
+void pms_ctx::bump(const char* name) { field(name).version++; }
+
+// ---------------------------------------------------------------------------------------------
+// instrumentation: launch counting and optional per-family CUDA-event timing on the ctx stream
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Timed {
+  pms_ctx* c;
+  int fam;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Timed(pms_ctx* cc, int f, int nlaunch = 1) : c(cc), fam(f) {
+    c->launches += nlaunch;
+    c->fam_launches[fam] += nlaunch;
+    if (c->timing) {
+      auto get = [&]() {
+        cudaEvent_t e;
+        if (!c->event_pool.empty()) {
+          e = c->event_pool.back();
+          c->event_pool.pop_back();
+        } else
+          cudaEventCreate(&e);
+        return e;
+      };
+      a = get();
+      b = get();
+      cudaEventRecord(a, c->stream);
+    }
+  }
+  ~Timed() {
+    if (a) {
+      cudaEventRecord(b, c->stream);
+      c->pending.push_back({fam, a, b});
+    }
+  }
+};
+
+void drain_timing(pms_ctx* c) {
+  if (c->pending.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto& p : c->pending) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    c->fam_ms[p.fam] += ms;
+    c->event_pool.push_back(p.a);
+    c->event_pool.push_back(p.b);
+  }
+  c->pending.clear();
+}
+
+void check_launch(pms_ctx* c, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw PmsError(PMS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  (void)c;
+}
+
+// copy reduction slots [slot, slot+nd) / [slot, slot+nu) to the host and wait
+void fetch(pms_ctx* c, int slot, int nd, int nu) {
+  if (nd) PMS_CUDA(cudaMemcpyAsync(c->h_out_d + slot, c->R.out_d + slot, nd * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (nu)
+    PMS_CUDA(cudaMemcpyAsync(c->h_out_u + slot, c->R.out_u + slot, nu * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             c->stream));
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (the process may already hold torch's libnccl.so.2)
+// ---------------------------------------------------------------------------------------------
+struct Uid {
+  char internal[128];
+};
+struct Nccl {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Uid, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+constexpr int NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3;
+
+void nccl_load() {
+  if (g_nccl.h) return;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) throw PmsError(PMS_ERR_NCCL, std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+#define SYM(field, name)                                                                   \
+  *(void**)(&g_nccl.field) = dlsym(g_nccl.h, name);                                        \
+  if (!g_nccl.field) throw PmsError(PMS_ERR_NCCL, std::string("NCCL symbol missing: ") + name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+}
+#define PMS_NCCL(call)                                                                                             \
+  do {                                                                                                             \
+    int r_ = (call);                                                                                               \
+    if (r_ != 0) throw PmsError(PMS_ERR_NCCL, std::string(#call) + " failed: " + g_nccl.GetErrorString(r_));       \
+  } while (0)
+
+// all-reduce n host doubles in place (line-search / CG scalars; replaces stk::all_reduce, Def.hpp:379-385 etc.)
+void allreduce(pms_ctx* c, double* v, int n, int op) {
+  if (c->nranks <= 1) return;
+  PMS_CUDA(cudaMemcpyAsync(c->d_coll, v, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  {
+    Timed t(c, FAM_HALO);
+    PMS_NCCL(g_nccl.AllReduce(c->d_coll, c->d_coll, n, NCCL_F64, op, c->nccl_comm, c->stream));
+  }
+  PMS_CUDA(cudaMemcpyAsync(v, c->d_coll, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+template <class T>
+T* dalloc(size_t n) {
+  T* p = nullptr;
+  PMS_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return p;
+}
+template <class T>
+T* dupload(const std::vector<T>& v) {
+  T* p = dalloc<T>(v.size());
+  if (!v.empty()) PMS_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return p;
+}
+
+void require_committed(pms_ctx* c) {
+  if (!c->committed) throw PmsError(PMS_ERR_ARG, "pms_commit has not been called");
+}
+
+// device_safe_transform_block_indices, MeshType.hpp:86-131
+void transform_block_indices(const int idx[3], const int tr[3], const int lbeg[3], const int dbeg[3], int donor[3]) {
+  int t[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) t[3 * i + j] = (tr[j] < 0 ? -1 : 1) * (int)(std::abs(tr[j]) == i + 1);
+  const int diff[3] = {idx[0] - lbeg[0], idx[1] - lbeg[1], idx[2] - lbeg[2]};
+  for (int r = 0; r < 3; r++) donor[r] = t[3 * r] * diff[0] + t[3 * r + 1] * diff[1] + t[3 * r + 2] * diff[2] + dbeg[r];
+}
+
+// interface-node ownership for dots / node counts: BlockStructuredGrid.cpp:448-458, BlockStructuredGrid.hpp:156-300
+bool sgrid_node_counted(const HBlock& B, int blockID, unsigned i, unsigned j, unsigned k) {
+  const bool on_end = (i == 0 || i == B.n[0] - 1 || j == 0 || j == B.n[1] - 1 || k == 0 || k == B.n[2] - 1);
+  if (!on_end) return true;
+  bool inAny = false;
+  unsigned min_block = blockID;
+  for (const HZone& z : B.zones) {
+    unsigned lb[3], le[3];
+    for (int d = 0; d < 3; d++) {
+      lb[d] = std::min(z.owner_beg[d], z.owner_end[d]) - 1;
+      le[d] = std::max(z.owner_beg[d], z.owner_end[d]) - 1;
+    }
+    if (lb[0] <= i && i <= le[0] && lb[1] <= j && j <= le[1] && lb[2] <= k && k <= le[2]) {
+      inAny = true;
+      if (min_block > (unsigned)z.donor) min_block = z.donor;
+    }
+  }
+  if (!inAny) return true;
+  return min_block == (unsigned)blockID;
+}
+
+long long find_root(std::vector<long long>& parent, long long a) {
+  while (parent[a] != a) {
+    parent[a] = parent[parent[a]];
+    a = parent[a];
+  }
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// operations shared by the C ABI and the CG driver
+// ---------------------------------------------------------------------------------------------
+void invalidate_cache(pms_ctx* c) { c->cache.clear(); }
+
+void op_copy(pms_ctx* c, const char* dst, const char* src) {
+  DField& d = c->field(dst);
+  DField& s = c->field(src);
+  if (d.ncomp != s.ncomp) throw PmsError(PMS_ERR_ARG, "copy_field: component mismatch");
+  Timed t(c, FAM_BLAS1);
+  PMS_CUDA(cudaMemcpyAsync(d.d, s.d, (size_t)d.ncomp * c->Npad * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  d.version++;
+}
+
+double op_dot(pms_ctx* c, const char* x, const char* y) {
+  DField& fx = c->field(x);
+  DField& fy = c->field(y);
+  if (fx.ncomp != fy.ncomp) throw PmsError(PMS_ERR_ARG, "nodal_field_dot: component mismatch");
+  {
+    Timed t(c, FAM_BLAS1);
+    c->L->dot(c->stream, fx.d, fy.d, c->dotmask_trivial ? nullptr : c->d_dotmask, c->N, c->Npad, fx.ncomp, c->R, 0);
+    check_launch(c, "dot");
+  }
+  fetch(c, 0, 1, 0);
+  double v = c->h_out_d[0];
+  allreduce(c, &v, 1, NCCL_SUM);
+  return v;
+}
+
+void halo_exchange(pms_ctx* c, const char* name);
+
+// total_metric(alpha), Def.hpp:330-388, without materialising x + alpha*s
+void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t* ninv, bool count_eval = true) {
+  DField& X = c->field("coordinates");
+  DField& S = c->field("cg_s");
+  DField& W = c->field("coordinates_NM1");
+  const bool with_s = alpha != 0.0;
+  if (c->cache_metric && !c->keep_elem) {
+    for (auto& e : c->cache)
+      if (e.xv == X.version && e.wv == W.version && e.stage == stage && e.alpha == alpha && e.use_ref == c->use_ref_mesh &&
+          (!with_s || e.sv == S.version)) {
+        *mtot = e.mtot;
+        if (ninv) *ninv = e.ninv;
+        return;
+      }
+  }
+  const int nb = (int)c->dev_blocks.size();
+  if (nb > pms_ctx::NSLOT) throw PmsError(PMS_ERR_ARG, "too many structured blocks in one ctx");
+  for (int b = 0; b < nb; b++) {
+    Timed t(c, FAM_METRIC);
+    c->L->metric(c->stream, c->dev_blocks[b], stage, c->use_ref_mesh ? 1 : 0, X.d, with_s ? S.d : nullptr, W.d, c->Npad,
+                 alpha, c->R, b, c->keep_elem ? c->d_elem_metric : nullptr, c->keep_elem ? c->d_elem_flag : nullptr);
+    check_launch(c, "metric");
+  }
+  fetch(c, 0, nb, nb);
+  double m = 0.0;  // per-block results added in block order (Def.hpp:355-360)
+  uint64_t n = 0;
+  for (int b = 0; b < nb; b++) {
+    m += c->h_out_d[b];
+    n += c->h_out_u[b];
+  }
+  if (c->nranks > 1) {
+    double v[2] = {m, (double)n};
+    allreduce(c, v, 2, NCCL_SUM);
+    m = v[0];
+    n = (uint64_t)v[1];
+  }
+  *mtot = m;
+  if (ninv) *ninv = n;
+  (void)count_eval;
+  if (c->cache_metric) {
+    if (c->cache.size() >= 8) c->cache.erase(c->cache.begin());
+    c->cache.push_back({X.version, S.version, W.version, stage, alpha, m, n, c->use_ref_mesh});
+  }
+}
+
+void ensure_eg(pms_ctx* c) {
+  if (!c->d_eg) c->d_eg = dalloc<double>((size_t)3 * (c->topo == 4 ? 4 : 8) * c->Epad);
+}
+
+// get_gradient (Def.hpp:1481-1520); optionally the fused metric of the same pass
+void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv) {
+  DField& X = c->field("coordinates");
+  DField& W = c->field("coordinates_NM1");
+  DField& G = c->field("cg_g");
+  DField& Rr = c->field("cg_r");
+  const int nb = (int)c->dev_blocks.size();
+  // structured: get_gradient() never forwards m_use_ref_mesh to m_sgrid_gradient (Def.hpp:1485-1495) => always ref mesh
+  const int use_ref = c->structured ? 1 : (c->use_ref_mesh ? 1 : 0);
+  bool fused_ok = false;
+  if (c->structured) {
+    fused_ok = true;
+    for (int b = 0; b < nb && fused_ok; b++) {
+      Timed t(c, FAM_GRADIENT);
+      fused_ok = c->L->grad_fused_sgrid(c->stream, c->dev_blocks[b], stage, X.d, W.d, c->Npad, c->d_fixed, G.d, c->R, b);
+      if (!fused_ok) {
+        c->launches--;
+        c->fam_launches[FAM_GRADIENT]--;
+      }
+    }
+  }
+  if (!fused_ok) {
+    ensure_eg(c);
+    for (int b = 0; b < nb; b++) {
+      Timed t(c, FAM_GRADIENT, 2);
+      c->L->grad_elements(c->stream, c->dev_blocks[b], stage, use_ref, X.d, W.d, c->Npad, c->d_eg, c->Epad, c->R, b,
+                          c->keep_elem ? c->d_elem_metric : nullptr, c->keep_elem ? c->d_elem_flag : nullptr);
+      check_launch(c, "grad_elements");
+      c->L->grad_gather(c->stream, c->dev_blocks[b], c->d_eg, c->Epad, c->d_fixed, c->structured ? nullptr : c->d_node_owned,
+                        G.d, c->structured ? nullptr : Rr.d, c->Npad);
+      check_launch(c, "grad_gather");
+    }
+  }
+  if (c->n_groups > 0) {  // inter-block sum + propagate, gradient_functors.hpp:479-482
+    Timed t(c, FAM_GRADIENT);
+    c->L->group_sum(c->stream, c->n_groups, c->d_grp_ptr, c->d_grp_nodes, G.d, 3, c->Npad);
+    check_launch(c, "group_sum");
+  }
+  G.version++;
+  if (!c->structured) Rr.version++;
+  if (mtot) {
+    fetch(c, 0, nb, nb);
+    double m = 0.0;
+    uint64_t n = 0;
+    for (int b = 0; b < nb; b++) {
+      m += c->h_out_d[b];
+      n += c->h_out_u[b];
+    }
+    if (c->nranks > 1) {
+      double v[2] = {m, (double)n};
+      allreduce(c, v, 2, NCCL_SUM);
+      m = v[0];
+      n = (uint64_t)v[1];
+    }
+    *mtot = m;
+    if (ninv) *ninv = n;
+    // the fused value is the metric at alpha = 0 with the gradient's use_ref flag
+    if (c->cache_metric && use_ref == (c->use_ref_mesh ? 1 : 0)) {
+      if (c->cache.size() >= 8) c->cache.erase(c->cache.begin());
+      c->cache.push_back({X.version, c->field("cg_s").version, W.version, stage, 0.0, m, n, c->use_ref_mesh});
+    }
+  }
+}
+
+void op_edge_lengths(pms_ctx* c) {
+  DField& W = c->field("coordinates_NM1");
+  DField& EL = c->field("cg_edge_length");
+  DField& NA = c->field("num_adj_elems");
+  for (auto& mb : c->dev_blocks) {
+    Timed t(c, FAM_EDGE);
+    c->L->edge_lengths(c->stream, mb, W.d, c->Npad, EL.d, NA.d);
+    check_launch(c, "edge_lengths");
+  }
+  if (c->structured) {
+    if (c->n_groups > 0) {  // sum + propagate across interfaces, get_edge_len_avg.hpp:333-341
+      Timed t(c, FAM_EDGE, 2);
+      c->L->group_sum(c->stream, c->n_groups, c->d_grp_ptr, c->d_grp_nodes, EL.d, 1, c->Npad);
+      c->L->group_sum(c->stream, c->n_groups, c->d_grp_ptr, c->d_grp_nodes, NA.d, 1, c->Npad);
+    }
+    Timed t(c, FAM_EDGE);
+    c->L->divide(c->stream, EL.d, NA.d, c->N);
+    check_launch(c, "divide");
+  }
+  EL.version++;
+  NA.version++;
+}
+
+double op_alpha0(pms_ctx* c) {
+  DField& S = c->field("cg_s");
+  DField& EL = c->field("cg_edge_length");
+  {
+    Timed t(c, FAM_ALPHA0);
+    // structured: all nodes (get_alpha_0_refmesh.hpp:168-193); STK: skip fixed nodes (Def.hpp:876-878)
+    c->L->alpha0(c->stream, S.d, EL.d, c->structured ? nullptr : c->d_fixed, c->N, c->Npad, c->R, 0);
+    check_launch(c, "alpha0");
+  }
+  fetch(c, 0, 1, 0);
+  double a = c->h_out_d[0];
+  allreduce(c, &a, 1, NCCL_MIN);
+  if (a == DBL_MAX) a = 1.0;  // nothing moves: get_alpha_0_refmesh.hpp:164-165, Def.hpp:851-852
+  if (!(a > 0.0)) throw PmsError(PMS_ERR_SMOOTHER, "bad alpha");
+  return a;
+}
+
+void op_update(pms_ctx* c, double alpha, double* dmax, double* dmax_rel) {
+  DField& X = c->field("coordinates");
+  DField& LG = c->field("coordinates_lagged");
+  DField& S = c->field("cg_s");
+  DField& EL = c->field("cg_edge_length");
+  {
+    Timed t(c, FAM_UPDATE);
+    c->L->update(c->stream, X.d, LG.d, S.d, EL.d, c->d_fixed, alpha, c->N, c->Npad, c->R, 0);
+    check_launch(c, "update");
+  }
+  X.version++;
+  LG.version++;
+  fetch(c, 0, 2, 0);
+  double v[2] = {c->h_out_d[0], c->h_out_d[1]};
+  allreduce(c, v, 2, NCCL_MAX);
+  *dmax = v[0];
+  *dmax_rel = v[1];
+}
+
+uint64_t op_count_invalid(pms_ctx* c) {  // MeshSmoother.cpp:192-234: untangle metric's valid flag
+  double m;
+  uint64_t n;
+  op_total_metric(c, 0, 0.0, &m, &n);
+  return n;
+}
+
+void halo_exchange(pms_ctx* c, const char* name) {
+  if (c->nranks <= 1 || c->nb_ranks.empty()) return;
+  DField& F = c->field(name);
+  const int nc = F.ncomp;
+  const int nn = (int)c->nb_ranks.size();
+  Timed t(c, FAM_HALO, 2 * nn);
+  for (int q = 0; q < nn; q++) {
+    const long long cnt = c->send_off[q + 1] - c->send_off[q];
+    c->L->pack(c->stream, F.d, c->Npad, nc, c->d_send_nodes + c->send_off[q], cnt, c->d_send_buf + 3 * c->send_off[q]);
+  }
+  PMS_NCCL(g_nccl.GroupStart());
+  for (int q = 0; q < nn; q++) {
+    const long long sc = c->send_off[q + 1] - c->send_off[q], rc = c->recv_off[q + 1] - c->recv_off[q];
+    if (sc) PMS_NCCL(g_nccl.Send(c->d_send_buf + 3 * c->send_off[q], sc * nc, NCCL_F64, c->nb_ranks[q], c->nccl_comm, c->stream));
+    if (rc) PMS_NCCL(g_nccl.Recv(c->d_recv_buf + 3 * c->recv_off[q], rc * nc, NCCL_F64, c->nb_ranks[q], c->nccl_comm, c->stream));
+  }
+  PMS_NCCL(g_nccl.GroupEnd());
+  for (int q = 0; q < nn; q++) {
+    const long long cnt = c->recv_off[q + 1] - c->recv_off[q];
+    c->L->unpack(c->stream, F.d, c->Npad, nc, c->d_recv_nodes + c->recv_off[q], cnt, c->d_recv_buf + 3 * c->recv_off[q]);
+  }
+  check_launch(c, "halo");
+  F.version++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CG driver (host control flow; Double = double)
+// ---------------------------------------------------------------------------------------------
+struct Driver {
+  pms_ctx* c;
+  pms_state* st;
+  double gradNorm;
+  Driver(pms_ctx* cc, pms_state* s, double gn) : c(cc), st(s), gradNorm(gn) {}
+
+  double tm(double alpha, bool& valid, uint64_t* ninv = nullptr) {
+    double m;
+    uint64_t n;
+    const uint64_t before = c->fam_launches[FAM_METRIC];
+    op_total_metric(c, st->stage, alpha, &m, &n);
+    if (c->fam_launches[FAM_METRIC] != before) st->n_metric_evals++;
+    valid = (n == 0);
+    if (ninv) *ninv = n;
+    return m;
+  }
+
+  void s_equals_r() {  // copy_field(cg_s, cg_r)
+    op_copy(c, "cg_s", "cg_r");
+    halo_exchange(c, "cg_s");
+  }
+
+  // line_search, Def.hpp:466-591
+  double line_search(bool& restarted) {
+    const double alpha_fac = 10.0, tau = 0.5, c0 = 1.e-1, min_alpha_factor = 1.e-12;
+    st->alpha_0 = op_alpha0(c);
+    double alpha = alpha_fac * st->alpha_0;
+    bool total_valid = false;
+    uint64_t n_invalid = 0;
+    const double metric_0 = tm(0.0, total_valid, &n_invalid);
+    double metric = 0.0;
+    double sDotGrad = op_dot(c, "cg_s", "cg_g");
+    if (sDotGrad >= 0.0) {
+      s_equals_r();
+      st->alpha_0 = op_alpha0(c);
+      alpha = alpha_fac * st->alpha_0;
+      sDotGrad = op_dot(c, "cg_s", "cg_g");
+      restarted = true;
+    }
+    if (!(sDotGrad < 0.0)) throw PmsError(PMS_ERR_SMOOTHER, "bad sDotGrad");
+    const double armijo_offset_factor = c0 * sDotGrad;
+    bool converged = false;
+    total_valid = false;
+    int liter = 0;
+    const int niter = 1000;
+    while (!converged && liter < niter) {
+      metric = tm(alpha, total_valid, &n_invalid);
+      const double mfac = alpha * armijo_offset_factor * 1.0;
+      converged = (metric < metric_0 + mfac);
+      if (st->untangled) converged = converged && total_valid;
+      if (!converged) {
+        alpha *= tau;
+        st->n_line_search_halvings++;
+      }
+      if (alpha < min_alpha_factor * st->alpha_0) break;
+      ++liter;
+    }
+    if (!converged) {
+      restarted = true;
+      s_equals_r();
+      st->alpha_0 = op_alpha0(c);
+      alpha = alpha_fac * st->alpha_0;
+      sDotGrad = op_dot(c, "cg_s", "cg_g");
+      if (!(sDotGrad < 0.0)) throw PmsError(PMS_ERR_SMOOTHER, "bad sDotGrad 2nd time");
+    }
+    liter = 0;
+    while (!converged && liter < niter) {
+      metric = tm(alpha, total_valid);
+      const double mfac = alpha * armijo_offset_factor;
+      converged = (metric < metric_0 + mfac);
+      if (st->untangled) {
+        converged = converged && total_valid;
+        if (total_valid && st->dmax_relative < gradNorm) converged = true;
+      }
+      if (!converged) {
+        alpha *= tau;
+        st->n_line_search_halvings++;
+      }
+      if (alpha < min_alpha_factor * st->alpha_0) break;
+      ++liter;
+    }
+    if (!converged) throw PmsError(PMS_ERR_SMOOTHER, "can't reduce metric");
+    const double a1 = alpha / 2., a2 = alpha;
+    const double f0 = metric_0, f1 = tm(a1, total_valid), f2 = tm(a2, total_valid);
+    const double den = 2. * (a2 * (-f0 + f1) + a1 * (f0 - f2));
+    const double num = a2 * a2 * (f1 - f0) + a1 * a1 * (f0 - f2);
+    if (std::fabs(den) > 1.e-10) {
+      const double alpha_quadratic = num / den;
+      if (alpha_quadratic > 1.e-10 && alpha_quadratic < 2 * alpha) {
+        const double fm = tm(alpha_quadratic, total_valid);
+        if (fm < f2 && (st->stage == 0 || total_valid)) alpha = alpha_quadratic;
+      }
+    }
+    return alpha;
+  }
+
+  bool check_convergence() const { return pms_check_convergence(st, gradNorm) != 0; }
+
+  // run_one_iteration, Def.hpp:1010-1093
+  double run_one_iteration() {
+    bool total_valid = false;
+    if (st->iter == 0) {
+      op_edge_lengths(c);
+      for (const char* nm : {"cg_r", "cg_d", "cg_s"}) {
+        DField& f = c->field(nm);
+        Timed t(c, FAM_BLAS1);
+        c->L->set_value(c->stream, f.d, 0.0, c->N, c->Npad, 3);
+        f.version++;
+      }
+    }
+    // f'(x) (+ the metric at the same x from the same pass, which is what metric_check evaluates)
+    {
+      double m;
+      uint64_t n;
+      op_gradient(c, st->stage, &m, &n);
+      st->n_gradient_evals++;
+    }
+    // r = -g ; dold = d.d ; dmid = r.d ; dnew = r.r   (Def.hpp:1034-1037)
+    {
+      DField& G = c->field("cg_g");
+      DField& D = c->field("cg_d");
+      DField& Rr = c->field("cg_r");
+      {
+        Timed t(c, FAM_BLAS1);
+        c->L->cg_r_dots(c->stream, G.d, D.d, Rr.d, c->dotmask_trivial ? nullptr : c->d_dotmask, c->N, c->Npad, c->R, 0);
+        check_launch(c, "cg_r_dots");
+      }
+      Rr.version++;
+      fetch(c, 0, 3, 0);
+      double v[3] = {c->h_out_d[0], c->h_out_d[1], c->h_out_d[2]};
+      allreduce(c, v, 3, NCCL_SUM);
+      st->dold = v[0];
+      st->dmid = v[1];
+      st->dnew = v[2];
+    }
+    if (st->iter == 0) st->d0 = st->dnew;
+    const double metric_check = tm(0.0, total_valid);
+    st->total_metric = metric_check;
+    if (check_convergence() || metric_check == 0.0) return tm(0.0, total_valid);
+
+    double cg_beta = 0.0;
+    if (st->dold == 0.0)
+      cg_beta = 0.0;
+    else if (st->iter > 0)
+      cg_beta = (st->dnew - st->dmid) / st->dold;
+    const uint64_t N = st->num_nodes;
+    const bool restart = (N == 0 || (uint64_t)st->iter % N == 0 || cg_beta <= 0.0);
+    {
+      DField& Rr = c->field("cg_r");
+      DField& S = c->field("cg_s");
+      DField& D = c->field("cg_d");
+      Timed t(c, FAM_BLAS1);
+      c->L->cg_s_update(c->stream, Rr.d, S.d, D.d, cg_beta, restart ? 1 : 0, c->N, c->Npad);
+      check_launch(c, "cg_s_update");
+      S.version++;
+      D.version++;
+    }
+    halo_exchange(c, "cg_s");
+    bool restarted = false;
+    const double alpha = line_search(restarted);
+    st->restarted += restarted ? 1 : 0;
+    const double snorm = op_dot(c, "cg_s", "cg_s");
+    st->grad_norm_scaled = st->alpha_0 * std::sqrt(snorm) / double(st->num_nodes);
+    st->alpha = alpha;
+    op_update(c, alpha, &st->dmax, &st->dmax_relative);  // update_node_positions, Def.hpp:395-410
+    return tm(0.0, total_valid);
+  }
+
+  // run_algorithm, ReferenceMeshSmootherBase.cpp:240-334
+  void run_algorithm(int innerIter, const char* log_path) {
+    std::ofstream myFile;
+    const unsigned width = 14;
+    const bool log = log_path && c->rank == 0;
+    if (log) {  // ReferenceMeshSmootherBase.cpp:57-81
+      myFile.open(log_path, std::ios::out);
+      myFile.precision(6);
+      myFile.setf(std::ios_base::left, std::ios_base::adjustfield);
+      myFile.setf(std::ios_base::scientific);
+      myFile << std::setw(8) << "%iter" << std::setw(width) << "global_metric" << std::setw(width) << "invalid_elems"
+             << std::setw(width) << "dmax" << std::setw(width) << "dmax_rel" << std::setw(width) << "grad/g0"
+             << std::setw(width) << "gradScaled" << std::setw(width) << "alpha" << std::setw(width) << "alpha_0"
+             << std::setw(6) << "stage" << std::setw(width) << "untangled_elems" << std::setw(width) << "noNodes"
+             << std::endl;
+    }
+    pms_state_init(c, st);
+    op_copy(c, "coordinates_lagged", "coordinates_NM1");
+    {  // coordinates = 1.0*coordinates_N + 0.0*coordinates_NM1 + 0.0*coordinates   (:259)
+      DField& X = c->field("coordinates");
+      Timed t(c, FAM_BLAS1);
+      c->L->axpbypgz(c->stream, 1.0, c->field("coordinates_N").d, 0.0, c->field("coordinates_NM1").d, 0.0, X.d, c->N, c->Npad, 3);
+      X.version++;
+    }
+    st->num_invalid = op_count_invalid(c);
+    st->untangled = (st->num_invalid == 0);
+    for (int stage = 0; stage < 2; stage++) {
+      st->stage = stage;
+      if (stage == 1) {
+        const uint64_t num_invalid_1 = op_count_invalid(c);
+        if (num_invalid_1 != 0) throw PmsError(PMS_ERR_SMOOTHER, "Invalid elements exist for start of stage 2, quiting");
+      }
+      for (int iter = 0; iter < innerIter; ++iter) {
+        st->iter = iter;
+        st->num_invalid = op_count_invalid(c);
+        const int num_invalid_0 = (int)st->num_invalid;
+        if (!st->untangled && st->num_invalid == 0) st->untangled = 1;
+        st->global_metric = run_one_iteration();
+        const bool conv = check_convergence();
+        st->converged = conv;
+        if (log) {  // print_iteration_status, :216-238
+          myFile << std::setw(8) << st->iter << std::setw(width) << st->global_metric << std::setw(width) << num_invalid_0
+                 << std::setw(width) << st->dmax << std::setw(width) << st->dmax_relative << std::setw(width)
+                 << std::sqrt(st->dnew / st->d0) << std::setw(width) << st->grad_norm_scaled << std::setw(width) << st->alpha
+                 << std::setw(width) << st->alpha_0 << std::setw(6) << st->stage << std::setw(width) << (bool)st->untangled
+                 << std::setw(width) << st->num_nodes << std::endl;
+        }
+        if (!st->untangled && st->num_invalid == 0) st->untangled = 1;
+        if (conv && st->untangled) break;
+      }
+    }
+    op_copy(c, "coordinates_lagged", "coordinates");
+  }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+#define PMS_TRY \
+  if (!c) return PMS_ERR_ARG; \
+  try {
+#define PMS_CATCH                   \
+  }                                 \
+  catch (const PmsError& e) {       \
+    c->err = e.what();              \
+    return e.code;                  \
+  }                                 \
+  catch (const std::exception& e) { \
+    c->err = e.what();              \
+    return PMS_ERR_ARG;             \
+  }                                 \
+  return PMS_OK;
+
+extern "C" {
+
+int pms_create(pms_ctx** out, int device) {
+  if (!out) return PMS_ERR_ARG;
+  *out = nullptr;
+  pms_ctx* c = new pms_ctx();
+  c->device = device;
+  try {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw PmsError(PMS_ERR_CUDA, std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                                       "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) throw PmsError(PMS_ERR_ARG, "device ordinal out of range");
+    PMS_CUDA(cudaSetDevice(device));
+    PMS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->L = pms_fast::launchers();
+  } catch (const PmsError& e) {
+    c->err = e.what();
+    *out = c;  // returned so the caller can read pms_last_error, then pms_destroy
+    return e.code;
+  }
+  *out = c;
+  return PMS_OK;
+}
+
+void pms_destroy(pms_ctx* c) {
+  if (!c) return;
+  if (c->stream) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->fields) cudaFree(kv.second.d);
+    void* ptrs[] = {c->d_conn,      c->d_fixed,     c->d_node_owned, c->d_elem_owned, c->d_dotmask,  c->d_elem_bits,
+                    c->d_csr_ptr,   c->d_csr_ent,   c->d_grp_ptr,    c->d_grp_nodes,  c->d_eg,       c->d_elem_metric,
+                    c->d_elem_flag, c->R.partial_d, c->R.partial_u,  c->R.ticket,     c->R.out_d,    c->R.out_u,
+                    c->d_send_nodes, c->d_recv_nodes, c->d_send_buf, c->d_recv_buf,   c->d_coll};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+    if (c->h_out_d) cudaFreeHost(c->h_out_d);
+    if (c->h_out_u) cudaFreeHost(c->h_out_u);
+    for (auto& p : c->pending) {
+      cudaEventDestroy(p.a);
+      cudaEventDestroy(p.b);
+    }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    cudaStreamDestroy(c->stream);
+  }
+  delete c;
+}
+
+const char* pms_last_error(const pms_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+
+int pms_set_option(pms_ctx* c, const char* key, double v) {
+  PMS_TRY
+  const std::string k(key);
+  if (k == "use_ref_mesh") {
+    c->use_ref_mesh = v != 0;
+  } else if (k == "strict_fp") {
+    c->strict_fp = v != 0;
+    c->L = c->strict_fp ? pms_strict::launchers() : pms_fast::launchers();
+    invalidate_cache(c);
+  } else if (k == "cache_metric") {
+    c->cache_metric = v != 0;
+    invalidate_cache(c);
+  } else if (k == "keep_element_metrics") {
+    c->keep_elem = v != 0;
+    if (c->keep_elem && c->committed && !c->d_elem_metric) {
+      c->d_elem_metric = dalloc<double>(c->Epad);
+      c->d_elem_flag = dalloc<int32_t>(c->Epad);
+    }
+  } else
+    throw PmsError(PMS_ERR_ARG, "unknown option " + k);
+  PMS_CATCH
+}
+
+int pms_add_structured_block(pms_ctx* c, const unsigned node_size[3], int* block_id) {
+  PMS_TRY
+  if (c->committed) throw PmsError(PMS_ERR_ARG, "mesh already committed");
+  if (!c->structured && c->topo != 0) throw PmsError(PMS_ERR_ARG, "ctx already holds an unstructured mesh");
+  for (int d = 0; d < 3; d++)
+    if (node_size[d] < 2) throw PmsError(PMS_ERR_ARG, "structured block needs >= 2 nodes per direction");
+  HBlock b;
+  for (int d = 0; d < 3; d++) b.n[d] = node_size[d];
+  c->structured = true;
+  c->blocks.push_back(b);
+  if (block_id) *block_id = (int)c->blocks.size() - 1;
+  PMS_CATCH
+}
+
+int pms_block_add_boundary_condition(pms_ctx* c, int block, const int rb[3], const int re[3]) {
+  PMS_TRY
+  if (block < 0 || block >= (int)c->blocks.size()) throw PmsError(PMS_ERR_ARG, "bad block id");
+  HBC bc;
+  for (int d = 0; d < 3; d++) {
+    bc.beg[d] = rb[d];
+    bc.end[d] = re[d];
+  }
+  c->blocks[block].bcs.push_back(bc);
+  PMS_CATCH
+}
+
+int pms_block_add_zone_connectivity(pms_ctx* c, int block, int donor, const int tr[3], const int ob[3], const int oe[3],
+                                    const int db[3], const int de[3]) {
+  PMS_TRY
+  if (block < 0 || block >= (int)c->blocks.size() || donor < 0) throw PmsError(PMS_ERR_ARG, "bad block id");
+  if (c->committed) throw PmsError(PMS_ERR_ARG, "mesh already committed");
+  HZone z;
+  z.donor = donor;
+  for (int d = 0; d < 3; d++) {
+    z.transform[d] = tr[d];
+    z.owner_beg[d] = ob[d];
+    z.owner_end[d] = oe[d];
+    z.donor_beg[d] = db[d];
+    z.donor_end[d] = de[d];
+  }
+  c->blocks[block].zones.push_back(z);
+  PMS_CATCH
+}
+
+int pms_set_unstructured(pms_ctx* c, int topology, size_t nnodes, size_t nelems, const int32_t* conn,
+                         const uint8_t* elem_owned, const uint8_t* node_owned) {
+  PMS_TRY
+  if (c->committed || c->structured) throw PmsError(PMS_ERR_ARG, "ctx already holds a mesh");
+  if (topology != PMS_HEX8 && topology != PMS_TET4) throw PmsError(PMS_ERR_ARG, "topology must be PMS_HEX8 or PMS_TET4");
+  if (!conn || nnodes == 0 || nelems == 0) throw PmsError(PMS_ERR_ARG, "empty mesh");
+  if (nnodes >= (1ull << 31)) throw PmsError(PMS_ERR_ARG, "more than 2^31 nodes per ctx");
+  c->topo = topology;
+  c->N = (long long)nnodes;
+  c->E = (long long)nelems;
+  c->h_conn.assign(conn, conn + nelems * topology);
+  for (int32_t v : c->h_conn)
+    if (v < 0 || (size_t)v >= nnodes) throw PmsError(PMS_ERR_ARG, "connectivity index out of range");
+  if (elem_owned) c->h_elem_owned.assign(elem_owned, elem_owned + nelems);
+  if (node_owned) c->h_node_owned.assign(node_owned, node_owned + nnodes);
+  PMS_CATCH
+}
+
+static long long total_nodes_precommit(pms_ctx* c) {
+  if (!c->structured) return c->N;
+  long long n = 0;
+  for (auto& b : c->blocks) n += b.nnodes();
+  return n;
+}
+
+int pms_set_fixed_mask(pms_ctx* c, const uint8_t* fixed) {
+  PMS_TRY
+  const long long n = total_nodes_precommit(c);
+  if (fixed)
+    c->h_fixed.assign(fixed, fixed + n);
+  else
+    c->h_fixed.assign(n, 0);
+  c->fixed_set = true;
+  if (c->committed) {
+    PMS_CUDA(cudaMemcpy(c->d_fixed, c->h_fixed.data(), n, cudaMemcpyHostToDevice));
+    for (auto& mb : c->dev_blocks) c->L->elem_fixed_bits(c->stream, mb, c->d_fixed, c->d_elem_bits);
+    check_launch(c, "elem_fixed_bits");
+    invalidate_cache(c);
+  }
+  PMS_CATCH
+}
+
+int pms_select_boundary_sgrid(pms_ctx* c) {  // SGridBoundarySelector, ReferenceMeshSmootherConjugateGradient.hpp:31-69
+  PMS_TRY
+  if (!c->structured) throw PmsError(PMS_ERR_ARG, "not a structured mesh");
+  long long N = 0;
+  for (auto& b : c->blocks) {
+    b.off = N;
+    N += b.nnodes();
+  }
+  std::vector<uint8_t> fx(N, 0);
+  for (auto& b : c->blocks)
+    for (const HBC& bc : b.bcs) {
+      long long beg[3], end[3];
+      for (int d = 0; d < 3; d++) {
+        beg[d] = std::min(bc.beg[d], bc.end[d]) - 1;
+        end[d] = std::max(bc.beg[d], bc.end[d]) - 1;
+        beg[d] = std::max<long long>(beg[d], 0);
+        end[d] = std::min<long long>(end[d], (long long)b.n[d] - 1);
+      }
+      for (long long k = beg[2]; k <= end[2]; k++)
+        for (long long j = beg[1]; j <= end[1]; j++)
+          for (long long i = beg[0]; i <= end[0]; i++) fx[b.node(i, j, k)] = 1;
+    }
+  return pms_set_fixed_mask(c, fx.data());
+  PMS_CATCH
+}
+
+int pms_commit(pms_ctx* c) {
+  PMS_TRY
+  if (c->committed) throw PmsError(PMS_ERR_ARG, "already committed");
+  if (!c->structured && c->topo == 0) throw PmsError(PMS_ERR_ARG, "no mesh defined");
+  PMS_CUDA(cudaSetDevice(c->device));
+  if (c->structured) {
+    long long off = 0, eoff = 0;
+    for (auto& b : c->blocks) {
+      b.off = off;
+      b.eoff = eoff;
+      off += b.nnodes();
+      eoff += b.ncells();
+    }
+    c->N = off;
+    c->E = eoff;
+    c->topo = 8;
+    for (auto& b : c->blocks)
+      for (auto& z : b.zones)
+        if (z.donor >= (int)c->blocks.size()) throw PmsError(PMS_ERR_ARG, "zone connectivity donor block does not exist");
+  }
+  if (c->N >= (1ll << 31)) throw PmsError(PMS_ERR_ARG, "more than 2^31 nodes per ctx");
+  c->Npad = (c->N + 31) / 32 * 32;
+  c->Epad = (c->E + 31) / 32 * 32;
+  if (!c->fixed_set) c->h_fixed.assign(c->N, 0);
+  if ((long long)c->h_fixed.size() != c->N) throw PmsError(PMS_ERR_ARG, "fixed mask length != node count");
+
+  // fields (add_coordinate_state_fields, PerceptMesh.cpp:4490-4539)
+  for (const char* n : FIELD_NAMES3) {
+    DField f;
+    f.ncomp = 3;
+    f.d = dalloc<double>((size_t)3 * c->Npad);
+    PMS_CUDA(cudaMemset(f.d, 0, (size_t)3 * c->Npad * sizeof(double)));
+    c->fields[n] = f;
+  }
+  for (const char* n : FIELD_NAMES1) {
+    DField f;
+    f.ncomp = 1;
+    f.d = dalloc<double>((size_t)c->Npad);
+    PMS_CUDA(cudaMemset(f.d, 0, (size_t)c->Npad * sizeof(double)));
+    c->fields[n] = f;
+  }
+  c->d_fixed = dalloc<uint8_t>(c->Npad);
+  PMS_CUDA(cudaMemset(c->d_fixed, 0, c->Npad));
+  PMS_CUDA(cudaMemcpy(c->d_fixed, c->h_fixed.data(), c->N, cudaMemcpyHostToDevice));
+  c->d_elem_bits = dalloc<uint8_t>(c->Epad);
+
+  // ownership masks for dots / node counts
+  c->h_dotmask.assign(c->N, 1);
+  c->dotmask_trivial = true;
+  if (c->structured) {
+    for (int ib = 0; ib < (int)c->blocks.size(); ib++) {
+      const HBlock& B = c->blocks[ib];
+      if (B.zones.empty()) continue;
+      for (unsigned k = 0; k < B.n[2]; k++)
+        for (unsigned j = 0; j < B.n[1]; j++)
+          for (unsigned i = 0; i < B.n[0]; i++)
+            if (!sgrid_node_counted(B, ib, i, j, k)) {
+              c->h_dotmask[B.node(i, j, k)] = 0;
+              c->dotmask_trivial = false;
+            }
+    }
+  } else if (!c->h_node_owned.empty()) {
+    c->h_dotmask = c->h_node_owned;
+    for (uint8_t v : c->h_dotmask)
+      if (!v) c->dotmask_trivial = false;
+  }
+  c->num_nodes_owned = 0;
+  for (uint8_t v : c->h_dotmask) c->num_nodes_owned += v ? 1 : 0;
+  if (!c->dotmask_trivial) {
+    c->d_dotmask = dalloc<uint8_t>(c->Npad);
+    PMS_CUDA(cudaMemset(c->d_dotmask, 0, c->Npad));
+    PMS_CUDA(cudaMemcpy(c->d_dotmask, c->h_dotmask.data(), c->N, cudaMemcpyHostToDevice));
+  }
+
+  // device mesh descriptors
+  c->dev_blocks.clear();
+  if (c->structured) {
+    for (auto& b : c->blocks) {
+      MeshDev m{};
+      m.kind = pmsk::KIND_SGRID;
+      m.ni = b.n[0];
+      m.nj = b.n[1];
+      m.nk = b.n[2];
+      m.node_off = b.off;
+      m.elem_off = b.eoff;
+      m.nnodes = b.nnodes();
+      m.nelems = b.ncells();
+      m.elem_fixed_bits = c->d_elem_bits;
+      c->dev_blocks.push_back(m);
+    }
+    // interface duplicate groups from the zone connectivities (union-find over flat node ids)
+    bool any_zone = false;
+    for (auto& b : c->blocks) any_zone = any_zone || !b.zones.empty();
+    if (any_zone) {
+      std::vector<long long> parent(c->N);
+      std::iota(parent.begin(), parent.end(), 0);
+      std::vector<uint8_t> touched(c->N, 0);
+      for (int ib = 0; ib < (int)c->blocks.size(); ib++) {
+        const HBlock& B = c->blocks[ib];
+        for (const HZone& z : B.zones) {
+          const HBlock& D = c->blocks[z.donor];
+          int lb[3], le[3];
+          for (int d = 0; d < 3; d++) {
+            lb[d] = std::min(z.owner_beg[d], z.owner_end[d]);
+            le[d] = std::max(z.owner_beg[d], z.owner_end[d]);
+          }
+          for (int k = lb[2]; k <= le[2]; k++)
+            for (int j = lb[1]; j <= le[1]; j++)
+              for (int i = lb[0]; i <= le[0]; i++) {
+                const int li[3] = {i, j, k};
+                int di[3];
+                transform_block_indices(li, z.transform, z.owner_beg, z.donor_beg, di);
+                for (int d = 0; d < 3; d++)
+                  if (di[d] < 1 || di[d] > (int)D.n[d]) throw PmsError(PMS_ERR_ARG, "zone connectivity maps outside the donor block");
+                const long long a = B.node(i - 1, j - 1, k - 1), bnode = D.node(di[0] - 1, di[1] - 1, di[2] - 1);
+                touched[a] = touched[bnode] = 1;
+                const long long ra = find_root(parent, a), rb = find_root(parent, bnode);
+                if (ra != rb) parent[std::max(ra, rb)] = std::min(ra, rb);
+              }
+        }
+      }
+      std::map<long long, std::vector<long long>> groups;
+      for (long long n = 0; n < c->N; n++)
+        if (touched[n]) groups[find_root(parent, n)].push_back(n);  // ascending n == ascending block id
+      std::vector<int64_t> gptr{0}, gnodes;
+      for (auto& kv : groups) {
+        if (kv.second.size() < 2) continue;
+        for (long long n : kv.second) gnodes.push_back(n);
+        gptr.push_back((int64_t)gnodes.size());
+      }
+      c->n_groups = (long long)gptr.size() - 1;
+      if (c->n_groups > 0) {
+        c->d_grp_ptr = dupload(gptr);
+        c->d_grp_nodes = dupload(gnodes);
+      }
+    }
+  } else {
+    const int npe = c->topo;
+    // SoA connectivity
+    std::vector<int32_t> soa((size_t)npe * c->Epad, 0);
+    for (long long e = 0; e < c->E; e++)
+      for (int a = 0; a < npe; a++) soa[(size_t)a * c->Epad + e] = c->h_conn[(size_t)e * npe + a];
+    c->d_conn = dupload(soa);
+    // node -> element CSR, entries sorted by (element, local node): deterministic gather order = ascending element id
+    c->h_csr_ptr.assign(c->N + 1, 0);
+    for (long long e = 0; e < c->E; e++)
+      for (int a = 0; a < npe; a++) c->h_csr_ptr[c->h_conn[(size_t)e * npe + a] + 1]++;
+    for (long long n = 0; n < c->N; n++) c->h_csr_ptr[n + 1] += c->h_csr_ptr[n];
+    c->h_csr_ent.assign(c->h_csr_ptr[c->N], 0);
+    {
+      std::vector<int64_t> fill(c->h_csr_ptr.begin(), c->h_csr_ptr.end() - 1);
+      for (long long e = 0; e < c->E; e++)
+        for (int a = 0; a < npe; a++) c->h_csr_ent[fill[c->h_conn[(size_t)e * npe + a]]++] = (int64_t)e * 8 + a;
+    }
+    c->d_csr_ptr = dupload(c->h_csr_ptr);
+    c->d_csr_ent = dupload(c->h_csr_ent);
+    if (!c->h_elem_owned.empty()) {
+      std::vector<uint8_t> eo(c->Epad, 0);
+      std::copy(c->h_elem_owned.begin(), c->h_elem_owned.end(), eo.begin());
+      c->d_elem_owned = dupload(eo);
+    }
+    if (!c->h_node_owned.empty()) {
+      std::vector<uint8_t> no(c->Npad, 0);
+      std::copy(c->h_node_owned.begin(), c->h_node_owned.end(), no.begin());
+      c->d_node_owned = dupload(no);
+    }
+    MeshDev m{};
+    m.kind = npe == 8 ? pmsk::KIND_HEX8 : pmsk::KIND_TET4;
+    m.nnodes = c->N;
+    m.nelems = c->E;
+    m.conn = c->d_conn;
+    m.conn_stride = c->Epad;
+    m.elem_fixed_bits = c->d_elem_bits;
+    m.elem_owned = c->d_elem_owned;
+    m.csr_ptr = c->d_csr_ptr;
+    m.csr_ent = c->d_csr_ent;
+    c->dev_blocks.push_back(m);
+  }
+
+  // reduction scratch: partial slots for the largest grid any kernel launches
+  long long maxb = 148 * 16;
+  for (auto& m : c->dev_blocks) {
+    long long nb = m.kind == pmsk::KIND_SGRID
+                       ? (long long)((m.ni + 30) / 32) * ((m.nj + 2) / 4) * ((m.nk + 0) / 2 + 1)
+                       : (m.nelems + 255) / 256;
+    maxb = std::max(maxb, nb + 8);
+  }
+  c->R.max_blocks = (int)maxb;
+  c->R.partial_d = dalloc<double>((size_t)3 * maxb);
+  c->R.partial_u = dalloc<unsigned long long>((size_t)maxb);
+  c->R.ticket = dalloc<unsigned int>(1);
+  PMS_CUDA(cudaMemset(c->R.ticket, 0, sizeof(unsigned int)));
+  c->R.out_d = dalloc<double>(pms_ctx::NSLOT);
+  c->R.out_u = dalloc<unsigned long long>(pms_ctx::NSLOT);
+  PMS_CUDA(cudaMallocHost(&c->h_out_d, pms_ctx::NSLOT * sizeof(double)));
+  PMS_CUDA(cudaMallocHost(&c->h_out_u, pms_ctx::NSLOT * sizeof(unsigned long long)));
+  c->d_coll = dalloc<double>(16);
+  if (c->keep_elem) {
+    c->d_elem_metric = dalloc<double>(c->Epad);
+    c->d_elem_flag = dalloc<int32_t>(c->Epad);
+  }
+  c->committed = true;
+  for (auto& mb : c->dev_blocks) c->L->elem_fixed_bits(c->stream, mb, c->d_fixed, c->d_elem_bits);
+  check_launch(c, "elem_fixed_bits");
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+  PMS_CATCH
+}
+
+int pms_num_nodes_local(const pms_ctx* c, size_t* n) {
+  if (!c || !n) return PMS_ERR_ARG;
+  *n = (size_t)(c->committed ? c->N : total_nodes_precommit(const_cast<pms_ctx*>(c)));
+  return PMS_OK;
+}
+int pms_num_elements_local(const pms_ctx* c, size_t* n) {
+  if (!c || !n) return PMS_ERR_ARG;
+  *n = (size_t)c->E;
+  return PMS_OK;
+}
+int pms_get_node_elem_csr(const pms_ctx* cc, int64_t* row_ptr, int64_t* entries) {
+  pms_ctx* c = const_cast<pms_ctx*>(cc);
+  PMS_TRY
+  require_committed(c);
+  if (c->structured) throw PmsError(PMS_ERR_ARG, "structured meshes use the implicit 8-cell stencil, no CSR");
+  memcpy(row_ptr, c->h_csr_ptr.data(), c->h_csr_ptr.size() * sizeof(int64_t));
+  memcpy(entries, c->h_csr_ent.data(), c->h_csr_ent.size() * sizeof(int64_t));
+  PMS_CATCH
+}
+
+static void block_range(pms_ctx* c, int block, long long& off, long long& n) {
+  if (block < 0) {
+    off = 0;
+    n = c->N;
+    return;
+  }
+  if (!c->structured || block >= (int)c->blocks.size()) throw PmsError(PMS_ERR_ARG, "bad block id");
+  off = c->blocks[block].off;
+  n = c->blocks[block].nnodes();
+}
+
+int pms_field_upload(pms_ctx* c, const char* name, int block, const double* host, int layout) {
+  PMS_TRY
+  require_committed(c);
+  DField& f = c->field(name);
+  long long off, n;
+  block_range(c, block, off, n);
+  if (layout == PMS_SOA) {
+    for (int k = 0; k < f.ncomp; k++)
+      PMS_CUDA(cudaMemcpyAsync(f.d + (size_t)k * c->Npad + off, host + (size_t)k * n, n * sizeof(double),
+                               cudaMemcpyHostToDevice, c->stream));
+    PMS_CUDA(cudaStreamSynchronize(c->stream));
+  } else if (layout == PMS_AOS) {
+    std::vector<double> tmp((size_t)f.ncomp * n);
+    for (int k = 0; k < f.ncomp; k++)
+      for (long long i = 0; i < n; i++) tmp[(size_t)k * n + i] = host[(size_t)i * f.ncomp + k];
+    for (int k = 0; k < f.ncomp; k++)
+      PMS_CUDA(cudaMemcpyAsync(f.d + (size_t)k * c->Npad + off, tmp.data() + (size_t)k * n, n * sizeof(double),
+                               cudaMemcpyHostToDevice, c->stream));
+    PMS_CUDA(cudaStreamSynchronize(c->stream));
+  } else
+    throw PmsError(PMS_ERR_ARG, "bad layout");
+  f.version++;
+  PMS_CATCH
+}
+
+int pms_field_download(pms_ctx* c, const char* name, int block, double* host, int layout) {
+  PMS_TRY
+  require_committed(c);
+  DField& f = c->field(name);
+  long long off, n;
+  block_range(c, block, off, n);
+  if (layout == PMS_SOA) {
+    for (int k = 0; k < f.ncomp; k++)
+      PMS_CUDA(cudaMemcpyAsync(host + (size_t)k * n, f.d + (size_t)k * c->Npad + off, n * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->stream));
+    PMS_CUDA(cudaStreamSynchronize(c->stream));
+  } else if (layout == PMS_AOS) {
+    std::vector<double> tmp((size_t)f.ncomp * n);
+    for (int k = 0; k < f.ncomp; k++)
+      PMS_CUDA(cudaMemcpyAsync(tmp.data() + (size_t)k * n, f.d + (size_t)k * c->Npad + off, n * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->stream));
+    PMS_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < f.ncomp; k++)
+      for (long long i = 0; i < n; i++) host[(size_t)i * f.ncomp + k] = tmp[(size_t)k * n + i];
+  } else
+    throw PmsError(PMS_ERR_ARG, "bad layout");
+  PMS_CATCH
+}
+
+int pms_field_device_ptr(pms_ctx* c, const char* name, double** dptr, size_t* comp_stride) {
+  PMS_TRY
+  require_committed(c);
+  DField& f = c->field(name);
+  *dptr = f.d;
+  *comp_stride = (size_t)c->Npad;
+  f.version++;  // the caller may write through the pointer
+  PMS_CATCH
+}
+
+int pms_copy_field(pms_ctx* c, const char* dst, const char* src) {
+  PMS_TRY
+  require_committed(c);
+  op_copy(c, dst, src);
+  if (c->nranks > 1) halo_exchange(c, dst);
+  PMS_CATCH
+}
+
+int pms_nodal_field_axpby(pms_ctx* c, double alpha, const char* x, double beta, const char* y) {
+  PMS_TRY
+  require_committed(c);
+  DField& fx = c->field(x);
+  DField& fy = c->field(y);
+  if (fx.ncomp != fy.ncomp) throw PmsError(PMS_ERR_ARG, "axpby: component mismatch");
+  {
+    Timed t(c, FAM_BLAS1);
+    c->L->axpby(c->stream, alpha, fx.d, beta, fy.d, c->N, c->Npad, fy.ncomp);
+    check_launch(c, "axpby");
+  }
+  fy.version++;
+  PMS_CATCH
+}
+
+int pms_nodal_field_axpbypgz(pms_ctx* c, double alpha, const char* x, double beta, const char* y, double gamma,
+                             const char* z) {
+  PMS_TRY
+  require_committed(c);
+  DField& fx = c->field(x);
+  DField& fy = c->field(y);
+  DField& fz = c->field(z);
+  if (fx.ncomp != fy.ncomp || fx.ncomp != fz.ncomp) throw PmsError(PMS_ERR_ARG, "axpbypgz: component mismatch");
+  {
+    Timed t(c, FAM_BLAS1);
+    c->L->axpbypgz(c->stream, alpha, fx.d, beta, fy.d, gamma, fz.d, c->N, c->Npad, fz.ncomp);
+    check_launch(c, "axpbypgz");
+  }
+  fz.version++;
+  PMS_CATCH
+}
+
+int pms_nodal_field_dot(pms_ctx* c, const char* x, const char* y, double* result) {
+  PMS_TRY
+  require_committed(c);
+  *result = op_dot(c, x, y);
+  PMS_CATCH
+}
+
+int pms_nodal_field_set_value(pms_ctx* c, const char* name, double value) {
+  PMS_TRY
+  require_committed(c);
+  DField& f = c->field(name);
+  {
+    Timed t(c, FAM_BLAS1);
+    c->L->set_value(c->stream, f.d, value, c->N, c->Npad, f.ncomp);
+    check_launch(c, "set_value");
+  }
+  f.version++;
+  PMS_CATCH
+}
+
+int pms_get_number_nodes(pms_ctx* c, size_t* n) {
+  PMS_TRY
+  require_committed(c);
+  double v = (double)c->num_nodes_owned;
+  allreduce(c, &v, 1, NCCL_SUM);
+  *n = (size_t)v;
+  PMS_CATCH
+}
+
+int pms_get_edge_lengths(pms_ctx* c) {
+  PMS_TRY
+  require_committed(c);
+  op_edge_lengths(c);
+  PMS_CATCH
+}
+
+int pms_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, size_t* n_invalid) {
+  PMS_TRY
+  require_committed(c);
+  if (stage != 0 && stage != 1) throw PmsError(PMS_ERR_ARG, "stage must be 0 (untangle) or 1 (ShapeB1)");
+  uint64_t n;
+  op_total_metric(c, stage, alpha, mtot, &n);
+  if (n_invalid) *n_invalid = (size_t)n;
+  PMS_CATCH
+}
+
+int pms_get_gradient(pms_ctx* c, int stage) {
+  PMS_TRY
+  require_committed(c);
+  if (stage != 0 && stage != 1) throw PmsError(PMS_ERR_ARG, "stage must be 0 (untangle) or 1 (ShapeB1)");
+  op_gradient(c, stage, nullptr, nullptr);
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+  PMS_CATCH
+}
+
+int pms_metric_and_gradient(pms_ctx* c, int stage, double* mtot, size_t* n_invalid) {
+  PMS_TRY
+  require_committed(c);
+  if (stage != 0 && stage != 1) throw PmsError(PMS_ERR_ARG, "stage must be 0 (untangle) or 1 (ShapeB1)");
+  double m;
+  uint64_t n;
+  op_gradient(c, stage, &m, &n);
+  if (c->structured && !c->use_ref_mesh) {
+    // the structured gradient always uses the reference mesh; the metric honours use_ref_mesh
+    op_total_metric(c, stage, 0.0, &m, &n);
+  }
+  if (mtot) *mtot = m;
+  if (n_invalid) *n_invalid = (size_t)n;
+  PMS_CATCH
+}
+
+int pms_count_invalid_elements(pms_ctx* c, size_t* n_invalid) {
+  PMS_TRY
+  require_committed(c);
+  *n_invalid = (size_t)op_count_invalid(c);
+  PMS_CATCH
+}
+
+int pms_get_alpha_0(pms_ctx* c, double* a) {
+  PMS_TRY
+  require_committed(c);
+  *a = op_alpha0(c);
+  PMS_CATCH
+}
+
+int pms_update_node_positions(pms_ctx* c, double alpha, double* dmax, double* dmax_rel) {
+  PMS_TRY
+  require_committed(c);
+  double a, b;
+  op_update(c, alpha, &a, &b);
+  if (dmax) *dmax = a;
+  if (dmax_rel) *dmax_rel = b;
+  PMS_CATCH
+}
+
+int pms_get_element_metrics(pms_ctx* c, double* metric, int32_t* flag) {
+  PMS_TRY
+  require_committed(c);
+  if (!c->d_elem_metric) throw PmsError(PMS_ERR_ARG, "option keep_element_metrics is off");
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+  if (metric) PMS_CUDA(cudaMemcpy(metric, c->d_elem_metric, c->E * sizeof(double), cudaMemcpyDeviceToHost));
+  if (flag) PMS_CUDA(cudaMemcpy(flag, c->d_elem_flag, c->E * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  PMS_CATCH
+}
+
+int pms_state_init(pms_ctx* c, pms_state* st) {
+  PMS_TRY
+  require_committed(c);
+  memset(st, 0, sizeof(*st));
+  st->d0 = 1;
+  st->global_metric = DBL_MAX;
+  size_t n;
+  pms_get_number_nodes(c, &n);
+  st->num_nodes = n;
+  PMS_CATCH
+}
+
+int pms_check_convergence(const pms_state* st, double gradNorm) {  // Def.hpp:989-1008
+  const double grad_check = gradNorm;
+  bool retval = false;
+  if (st->stage == 0 && (st->dnew == 0.0 || st->total_metric == 0.0))
+    retval = true;
+  else if (st->stage == 0 && st->num_invalid == 0 && (st->dmax_relative < grad_check))
+    retval = true;
+  else if (st->num_invalid == 0 &&
+           (st->iter > 10 && (st->dmax_relative < grad_check &&
+                              (st->dnew < grad_check * grad_check * st->d0 || st->grad_norm_scaled < grad_check))))
+    retval = true;
+  return retval ? 1 : 0;
+}
+
+int pms_run_one_iteration(pms_ctx* c, pms_state* st, double grad_norm, double* metric_out) {
+  PMS_TRY
+  require_committed(c);
+  Driver d(c, st, grad_norm);
+  const double m = d.run_one_iteration();
+  st->global_metric = m;
+  if (metric_out) *metric_out = m;
+  PMS_CATCH
+}
+
+int pms_run_algorithm(pms_ctx* c, int inner_iterations, double grad_norm, const char* log_path, pms_state* st) {
+  PMS_TRY
+  require_committed(c);
+  pms_state local;
+  Driver d(c, st ? st : &local, grad_norm);
+  d.run_algorithm(inner_iterations, log_path);
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+  PMS_CATCH
+}
+
+// ---- multi-GPU ----
+int pms_comm_unique_id(void* id128) {
+  try {
+    nccl_load();
+    if (g_nccl.GetUniqueId(id128) != 0) return PMS_ERR_NCCL;
+  } catch (...) {
+    return PMS_ERR_NCCL;
+  }
+  return PMS_OK;
+}
+
+int pms_comm_init(pms_ctx* c, const void* id128, int rank, int nranks) {
+  PMS_TRY
+  nccl_load();
+  PMS_CUDA(cudaSetDevice(c->device));
+  Uid uid;
+  memcpy(uid.internal, id128, 128);
+  PMS_NCCL(g_nccl.CommInitRank(&c->nccl_comm, nranks, uid, rank));
+  c->rank = rank;
+  c->nranks = nranks;
+  PMS_CATCH
+}
+
+int pms_set_halo(pms_ctx* c, int nn, const int* ranks, const int64_t* send_off, const int32_t* send_nodes,
+                 const int64_t* recv_off, const int32_t* recv_nodes) {
+  PMS_TRY
+  require_committed(c);
+  c->nb_ranks.assign(ranks, ranks + nn);
+  c->send_off.assign(send_off, send_off + nn + 1);
+  c->recv_off.assign(recv_off, recv_off + nn + 1);
+  const int64_t ns = c->send_off[nn], nr = c->recv_off[nn];
+  for (int64_t i = 0; i < ns; i++)
+    if (send_nodes[i] < 0 || send_nodes[i] >= c->N) throw PmsError(PMS_ERR_ARG, "halo send node out of range");
+  for (int64_t i = 0; i < nr; i++)
+    if (recv_nodes[i] < 0 || recv_nodes[i] >= c->N) throw PmsError(PMS_ERR_ARG, "halo recv node out of range");
+  std::vector<int32_t> s(send_nodes, send_nodes + ns), r(recv_nodes, recv_nodes + nr);
+  c->d_send_nodes = dupload(s);
+  c->d_recv_nodes = dupload(r);
+  c->d_send_buf = dalloc<double>((size_t)3 * ns);
+  c->d_recv_buf = dalloc<double>((size_t)3 * nr);
+  PMS_CATCH
+}
+
+int pms_halo_exchange(pms_ctx* c, const char* name) {
+  PMS_TRY
+  require_committed(c);
+  halo_exchange(c, name);
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+  PMS_CATCH
+}
+
+// ---- instrumentation ----
+int pms_launch_count(const pms_ctx* c, uint64_t* n) {
+  if (!c || !n) return PMS_ERR_ARG;
+  *n = c->launches;
+  return PMS_OK;
+}
+int pms_stream(const pms_ctx* c, void** s) {
+  if (!c || !s) return PMS_ERR_ARG;
+  *s = (void*)c->stream;
+  return PMS_OK;
+}
+int pms_synchronize(pms_ctx* c) {
+  PMS_TRY
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+  PMS_CATCH
+}
+static int family_of(const std::string& f) {
+  const char* names[FAM_COUNT] = {"metric", "gradient", "blas1", "update", "alpha0", "edge", "halo"};
+  for (int i = 0; i < FAM_COUNT; i++)
+    if (f == names[i]) return i;
+  return -1;
+}
+int pms_kernel_time_ms(pms_ctx* c, const char* family, double* ms, uint64_t* launches) {
+  PMS_TRY
+  const int f = family_of(family);
+  if (f < 0) throw PmsError(PMS_ERR_ARG, "unknown kernel family");
+  drain_timing(c);
+  if (ms) *ms = c->fam_ms[f];
+  if (launches) *launches = c->fam_launches[f];
+  PMS_CATCH
+}
+int pms_kernel_time_reset(pms_ctx* c) {
+  PMS_TRY
+  drain_timing(c);
+  for (int i = 0; i < FAM_COUNT; i++) {
+    c->fam_ms[i] = 0;
+    c->fam_launches[i] = 0;
+  }
+  PMS_CATCH
+}
+int pms_set_timing(pms_ctx* c, int enabled) {
+  PMS_TRY
+  drain_timing(c);
+  c->timing = enabled != 0;
+  PMS_CATCH
+}
+
+}  // extern "C"

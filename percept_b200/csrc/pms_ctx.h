@@ -1,0 +1,122 @@
+// pms_ctx.h — internal context of the C ABI (host side). Not installed.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/percept_smoother_c.h"
+#include "pms_kernels.h"
+
+struct PmsError : std::runtime_error {
+  int code;
+  PmsError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PMS_CUDA(call)                                                                                     \
+  do {                                                                                                     \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess)                                                                                 \
+      throw PmsError(PMS_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e_));             \
+  } while (0)
+
+struct HBC {
+  int beg[3], end[3];
+};
+struct HZone {
+  int donor;
+  int transform[3], owner_beg[3], owner_end[3], donor_beg[3], donor_end[3];
+};
+struct HBlock {
+  unsigned n[3];
+  long long off = 0, eoff = 0;
+  std::vector<HBC> bcs;
+  std::vector<HZone> zones;
+  long long nnodes() const { return (long long)n[0] * n[1] * n[2]; }
+  long long ncells() const { return (long long)(n[0] - 1) * (n[1] - 1) * (n[2] - 1); }
+  long long node(long long i, long long j, long long k) const { return off + i + (long long)n[0] * (j + (long long)n[1] * k); }
+};
+
+struct DField {
+  int ncomp = 0;
+  double* d = nullptr;
+  uint64_t version = 0;  // bumped on every write; keys the metric cache
+};
+
+enum Family { FAM_METRIC = 0, FAM_GRADIENT, FAM_BLAS1, FAM_UPDATE, FAM_ALPHA0, FAM_EDGE, FAM_HALO, FAM_COUNT };
+
+struct pms_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  const pmsk::Launchers* L = nullptr;
+  bool strict_fp = false, use_ref_mesh = true, cache_metric = true, keep_elem = false, timing = false;
+  bool structured = false, committed = false;
+
+  // mesh (host description)
+  std::vector<HBlock> blocks;
+  int topo = 0;
+  long long N = 0, Npad = 0, E = 0, Epad = 0;
+  std::vector<int32_t> h_conn;  // AoS as given
+  std::vector<uint8_t> h_fixed, h_node_owned, h_elem_owned, h_dotmask;
+  std::vector<int64_t> h_csr_ptr, h_csr_ent;
+  bool fixed_set = false, dotmask_trivial = true;
+  uint64_t num_nodes_owned = 0;
+
+  // device mesh
+  std::vector<pmsk::MeshDev> dev_blocks;  // one per structured block, or a single entry
+  int32_t* d_conn = nullptr;
+  uint8_t *d_fixed = nullptr, *d_node_owned = nullptr, *d_elem_owned = nullptr, *d_dotmask = nullptr, *d_elem_bits = nullptr;
+  int64_t *d_csr_ptr = nullptr, *d_csr_ent = nullptr;
+  int64_t *d_grp_ptr = nullptr, *d_grp_nodes = nullptr;
+  long long n_groups = 0;
+  double* d_eg = nullptr;  // element-gradient scratch [3*npe][Epad]
+  double* d_elem_metric = nullptr;
+  int32_t* d_elem_flag = nullptr;
+
+  std::map<std::string, DField> fields;
+
+  // reductions
+  pmsk::Reduce R{};
+  double* h_out_d = nullptr;              // pinned mirrors of R.out_d / R.out_u
+  unsigned long long* h_out_u = nullptr;
+  static constexpr int NSLOT = 64;
+
+  // metric cache (identical evaluations reuse the previous result)
+  struct CacheEnt {
+    uint64_t xv, sv, wv;
+    int stage;
+    double alpha, mtot;
+    uint64_t ninv;
+    bool use_ref;
+  };
+  std::vector<CacheEnt> cache;
+  bool adj_fixed = false;
+
+  // multi-GPU
+  void* nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+  std::vector<int> nb_ranks;
+  std::vector<int64_t> send_off, recv_off;
+  int32_t *d_send_nodes = nullptr, *d_recv_nodes = nullptr;
+  double *d_send_buf = nullptr, *d_recv_buf = nullptr;
+  double* d_coll = nullptr;  // small device buffer for scalar allreduces
+
+  // instrumentation
+  uint64_t launches = 0;
+  double fam_ms[FAM_COUNT] = {0};
+  uint64_t fam_launches[FAM_COUNT] = {0};
+  struct Pending {
+    int fam;
+    cudaEvent_t a, b;
+  };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> event_pool;
+
+  std::string err;
+
+  DField& field(const char* name);
+  void bump(const char* name);
+};

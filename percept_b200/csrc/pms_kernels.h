@@ -1,0 +1,94 @@
+// pms_kernels.h — host-callable launchers of the sm_100a kernels (internal; not part of the C ABI).
+//
+// The kernel translation unit pms_kernels.cu is compiled twice:
+//   namespace pms_fast   : default nvcc FMA contraction
+//   namespace pms_strict : -fmad=false, bit-comparable with the -ffp-contract=off CPU oracle
+// Both export the same launcher table.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace pmsk {
+
+enum : int { KIND_SGRID = 0, KIND_HEX8 = 1, KIND_TET4 = 2 };
+
+// One structured block, or the whole unstructured mesh.
+struct MeshDev {
+  int kind;
+  int ni, nj, nk;            // nodes per direction (structured)
+  long long node_off;        // first node of this block in the flat node arrays
+  long long elem_off;        // first element of this block in the flat element arrays
+  long long nnodes, nelems;  // of this block / mesh
+  const int32_t* conn;       // unstructured: SoA connectivity conn[a*conn_stride + e]
+  long long conn_stride;
+  const uint8_t* elem_fixed_bits;  // bit a set <=> local vertex a is a fixed node (indexed by flat element id)
+  const uint8_t* elem_owned;       // unstructured: 1 = locally owned element (metric sums these); may be null
+  const int64_t* csr_ptr;          // unstructured node->element CSR
+  const int64_t* csr_ent;          // entries elem*8+local, ascending
+};
+
+struct Reduce {  // scratch for deterministic two-level reductions (partials + last-block ticket)
+  double* partial_d;            // [3 * max_blocks]
+  unsigned long long* partial_u;  // [max_blocks]
+  unsigned int* ticket;         // zero-initialised, self-resetting
+  double* out_d;                // result slots (device)
+  unsigned long long* out_u;
+  int max_blocks;
+};
+
+struct Launchers {
+  // metric of (x + alpha*s on unfixed nodes) vs reference w; result: out_d[slot] = sum, out_u[slot] = #invalid.
+  // s may be null (alpha = 0).  elem_metric/elem_flag optional.
+  void (*metric)(cudaStream_t, const MeshDev&, int stage, int use_ref, const double* x, const double* s, const double* w,
+                 long long stride, double alpha, const Reduce&, int slot, double* elem_metric, int32_t* elem_flag);
+  // element pass of the gradient: eg[(a*3+r)*eg_stride + e] (zero where the element is dropped); fused metric like above.
+  void (*grad_elements)(cudaStream_t, const MeshDev&, int stage, int use_ref, const double* x, const double* w,
+                        long long stride, double* eg, long long eg_stride, const Reduce&, int slot, double* elem_metric,
+                        int32_t* elem_flag);
+  // node pass: g[r*stride+n] = sum of adjacent elements' contributions in ascending element order; 0 at fixed /
+  // non-owned nodes.  r_out (may be null) receives a copy (cg_r = cg_g on STK meshes).
+  void (*grad_gather)(cudaStream_t, const MeshDev&, const double* eg, long long eg_stride, const uint8_t* fixed,
+                      const uint8_t* node_owned, double* g, double* r_out, long long stride);
+  // fused structured gradient (one kernel: cell tile in shared memory + node gather); returns false if unsupported
+  bool (*grad_fused_sgrid)(cudaStream_t, const MeshDev&, int stage, const double* x, const double* w, long long stride,
+                           const uint8_t* fixed, double* g, const Reduce&, int slot);
+
+  // interface groups (multi-block structured): for group q, nodes grp_nodes[grp_ptr[q]..grp_ptr[q+1]) are duplicates of
+  // one physical node, ascending block id.  val = sum over duplicates (in that order), written back to all.
+  void (*group_sum)(cudaStream_t, long long ngroups, const int64_t* grp_ptr, const int64_t* grp_nodes, double* f, int ncomp,
+                    long long stride);
+
+  // BLAS-1 over [ncomp][stride] SoA fields, first n entries of every plane
+  void (*axpby)(cudaStream_t, double a, const double* x, double b, double* y, long long n, long long stride, int ncomp);
+  void (*axpbypgz)(cudaStream_t, double a, const double* x, double b, const double* y, double c, double* z, long long n,
+                   long long stride, int ncomp);
+  void (*set_value)(cudaStream_t, double* x, double v, long long n, long long stride, int ncomp);
+  // out_d[slot] = sum_{owned n} sum_c x*y
+  void (*dot)(cudaStream_t, const double* x, const double* y, const uint8_t* mask, long long n, long long stride, int ncomp,
+              const Reduce&, int slot);
+  // r = -g ; out_d[slot..slot+2] = d.d, r.d, r.r   (Def.hpp:1034-1037 fused)
+  void (*cg_r_dots)(cudaStream_t, const double* g, const double* d, double* r, const uint8_t* mask, long long n,
+                    long long stride, const Reduce&, int slot);
+  // restart ? s = r : s = r + beta*s ; d = r   (Def.hpp:1057-1069 fused)
+  void (*cg_s_update)(cudaStream_t, const double* r, double* s, double* d, double beta, int restart, long long n,
+                      long long stride);
+  // out_d[slot] = min over candidate nodes of edge/|s|, DBL_MAX if none (get_alpha_0_refmesh.hpp:168-193)
+  void (*alpha0)(cudaStream_t, const double* s, const double* edge, const uint8_t* skip_mask, long long n, long long stride,
+                 const Reduce&, int slot);
+  // lagged = x ; x += alpha*s (unfixed) ; out_d[slot] = dmax, out_d[slot+1] = dmax_relative
+  void (*update)(cudaStream_t, double* x, double* lagged, const double* s, const double* edge, const uint8_t* fixed,
+                 double alpha, long long n, long long stride, const Reduce&, int slot);
+  // edge lengths: el = sum over adjacent elements of mean edge length, na = adjacency count (division done by divide())
+  void (*edge_lengths)(cudaStream_t, const MeshDev&, const double* w, long long stride, double* el, double* na);
+  void (*divide)(cudaStream_t, double* el, const double* na, long long n);
+  // halo pack / unpack: buf[c*count + i] <-> f[c*stride + nodes[i]]
+  void (*pack)(cudaStream_t, const double* f, long long stride, int ncomp, const int32_t* nodes, long long count, double* buf);
+  void (*unpack)(cudaStream_t, double* f, long long stride, int ncomp, const int32_t* nodes, long long count, const double* buf);
+  // per-element bit mask of fixed vertices
+  void (*elem_fixed_bits)(cudaStream_t, const MeshDev&, const uint8_t* fixed, uint8_t* bits);
+};
+
+}  // namespace pmsk
+
+namespace pms_fast { const pmsk::Launchers* launchers(); }
+namespace pms_strict { const pmsk::Launchers* launchers(); }
