@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native Percept mesh-smoothing hot path.
+
+Metric (BASELINE.json): Melem metric+grad evals/s (and CG iterations/s) on a 256^3 hex mesh, fraction of the HBM
+roofline, 1/2/4/8 GPUs.  A *step* is one fused ShapeB1 metric+gradient evaluation (get_gradient + total_metric(0),
+SM/ReferenceMeshSmootherConjugateGradientDef.hpp:330-388,1481-1520) over the whole mesh.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nele 256]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload at N = 1 (config.workload): BASELINE config 3 — synthetic 256^3 unstructured hex8 mesh in Exodus order
+(16.78 M elements, 16.97 M nodes), unit cube, interior nodes randomly perturbed (glibc srand(1)/rand(), the
+reference test's build_perturbed_cube) by +-0.125 h so the mesh stays valid and every corner takes the full ShapeB1
+path; cube faces fixed.  N > 1 is a weak-scaling run: the cube grows to (256 px) x (256 py) x (256 pz) cells and is
+cut geometrically into px*py*pz boxes, one per GPU, each with one layer of ghost elements (owner-computes gradient,
+no gradient exchange; metric scalars go through ncclAllReduce).
+
+The JSON line carries: value (device-resident throughput), e2e (same metric through the C ABI with pinned HOST
+buffers: coordinates H2D, gradient + scalars D2H inside the timed region), roofline (algorithmic bytes / CUDA-event
+time of the metric+gradient kernels vs MEASURED_PEAKS.json), cpu_baseline (the CPU restatement of the reference's
+functors, OpenMP, timed on this box's host cores on a bounded sample), clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_NODE_MGRAD = 72   # read x (24) + read x_ref (24) + write g (24)   [SURVEY 8(d)]
+ALG_BYTES_PER_HEX8_CONN = 32    # int32 connectivity read once per element
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle-reason samples during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        clocks = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": clocks[len(clocks) // 2] if clocks else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(clocks)}
+
+
+def proc_grid(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(n) or (n, 1, 1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle OpenMP restatement) on this box's host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference(nele_sample, target_seconds, threads=None):
+    """Times {get_gradient ; total_metric(0)} of the CPU restatement on an nele_sample^3 hex8 mesh (same generator,
+    same perturbation amplitude in units of h).  Returns (elements/s, info dict)."""
+    import ctypes as C
+    import numpy as np
+    from percept_b200.capi import Api
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "liborc_omp.so"))
+    api = Api(lib, "orc_", product=False)
+    lib.orc_fixture_cube.argtypes = [C.c_uint] * 3 + [C.POINTER(C.c_double)] * 3
+    lib.orc_perturb_cube_rand.argtypes = [C.c_uint, C.c_double, C.c_uint, C.POINTER(C.c_double)]
+    lib.orc_bench_metric_and_gradient.restype = C.c_double
+    lib.orc_bench_metric_and_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_size_t),
+                                                  C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.orc_omp_max_threads.restype = C.c_int
+    ncores = threads or os.cpu_count() or 1
+    n, nn = nele_sample, nele_sample + 1
+    W = np.zeros((3, nn ** 3))
+    dp = C.POINTER(C.c_double)
+    lib.orc_fixture_cube(nn, nn, nn, (C.c_double * 3)(1, 1, 1), (C.c_double * 3)(0, 0, 0), W.ctypes.data_as(dp))
+    X = W.copy()
+    lib.orc_perturb_cube_rand(n, 0.25 / n, 1, X.ctypes.data_as(dp))
+    # same mesh builders as the GPU arm (numpy only, no oracle code on the product path and vice versa)
+    ci, cj, ck = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    ci, cj, ck = (a.transpose(2, 1, 0).reshape(-1) for a in (ci, cj, ck))
+    nid = lambda i, j, k: i + nn * (j + nn * k)
+    offs = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    conn = np.ascontiguousarray(np.stack([nid(ci + a, cj + b, ck + c) for a, b, c in offs], axis=1).astype(np.int32))
+    i = np.arange(nn)
+    m = (i[None, None, :] % n == 0) | (i[None, :, None] % n == 0) | (i[:, None, None] % n == 0)
+    c = api.create()
+    c.set_option("omp_threads", ncores)
+    c.set_unstructured(8, nn ** 3, conn)
+    c.set_fixed_mask(np.ascontiguousarray(m.reshape(-1).astype(np.uint8)))
+    c.commit()
+    c.upload("coordinates", X)
+    c.upload("coordinates_N", X)
+    c.upload("coordinates_NM1", W)
+    mt, ni, tm, tg = C.c_double(), C.c_size_t(), C.c_double(), C.c_double()
+
+    def run(reps):
+        return lib.orc_bench_metric_and_gradient(c.p, 1, reps, C.byref(mt), C.byref(ni), C.byref(tm), C.byref(tg))
+    run(1)  # warm-up (page faults, OpenMP team start)
+    t1 = run(1)
+    reps = max(1, min(200, int(target_seconds / max(t1, 1e-6))))
+    t = run(reps)
+    nelem = n ** 3
+    return nelem * reps / t, {"cores": ncores, "reps": reps, "seconds": t, "nele_sample": n, "metric": mt.value,
+                              "t_metric_s": tm.value, "t_gradient_s": tg.value,
+                              "omp_max_threads": lib.orc_omp_max_threads()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nsample = min(args.nele, 128)
+    # K timed steps, each a bounded sample (nsample^3 hexes) of the workload; warm-up inside cpu_reference
+    per_step_target = 1.0
+    t0 = time.time()
+    vals = []
+    info = None
+    for _ in range(max(1, min(args.steps, 10))):
+        v, info = cpu_reference(nsample, per_step_target)
+        vals.append(v)
+    v = sum(vals) / len(vals)
+    out = {
+        "impl": "reference", "metric": "Melem metric+grad evals/s", "value": v / 1e6, "unit": "Melem/s", "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": 1, "ms_per_step": 1e3 * (nsample ** 3) / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.nele}^3 unstructured hex8, random perturbation 0.125h (valid), ShapeB1 fused metric+gradient; "
+                               f"each step evaluates a {nsample}^3-hex sample of it on the host cores"},
+        "cpu_baseline": {"value": v / 1e6, "unit": "Melem/s", "cores": info["cores"], "kind": "port",
+                         "sample": f"{nsample}^3 hex8 x {info['reps']} evaluations per step, OpenMP restatement of the reference functors "
+                                   f"(oracle/liborc_omp.so; the reference itself needs Kokkos/Trilinos/STK and cannot be built here)"},
+        "e2e": {"value": v / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import percept_b200 as pb
+    from percept_b200 import fixtures as fx
+    from percept_b200 import partition as part
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.nele
+    px, py, pz = proc_grid(world)
+    NX, NY, NZ = n * px, n * py, n * pz
+    h = 1.0 / n  # every rank's box is a unit cube in its own frame: identical per-GPU work (weak scaling)
+
+    # ---- local mesh: owned n^3 box + one layer of ghost elements --------------------------------------------
+    t_setup = time.time()
+    lm = part.box_local_mesh((NX, NY, NZ), (px, py, pz), rank)
+    # coordinates: global fixture cube scaled so that h is the same for all N; perturbation from the rank-local
+    # glibc stream on the owned+ghost box is not globally consistent, so use the deterministic hash-free form:
+    # perturb the GLOBAL lattice with the sinusoid-free random generator evaluated per global node id.
+    W = lm.global_lattice_coords(h)
+    X = part.perturb_by_global_id(W, lm.node_gid, lm.node_on_global_boundary, 0.25 * h, seed=1) if world > 1 else None
+    if world == 1:
+        Wc = fx.cube(n + 1)
+        Xc = fx.perturb_rand(Wc, n + 1, 0.25 / n, 1)  # BASELINE config 3 generator (build_perturbed_cube stream)
+        W, X = Wc, Xc
+    ctx = pb.create(local_rank)
+    ctx.set_unstructured(pb.HEX8, lm.nnodes, lm.conn, lm.elem_owned if world > 1 else None, lm.node_owned if world > 1 else None)
+    ctx.set_fixed_mask(lm.node_on_global_boundary.astype(np.uint8))
+    ctx.commit()
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            import ctypes as C
+            buf = C.create_string_buffer(128)
+            assert pb.lib.pms_comm_unique_id(buf) == 0
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        ctx.set_halo(lm.nb_ranks, lm.send_off, lm.send_nodes, lm.recv_off, lm.recv_nodes)
+    ctx.upload("coordinates", X)
+    ctx.upload("coordinates_N", X)
+    ctx.upload("coordinates_NM1", W)
+    nel_owned = int(lm.n_owned_elems)
+    nnod_local = lm.nnodes
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.ExternalStream(ctx.stream())
+    STAGE = 1
+
+    # ---- (1) device-resident: K fused metric+gradient evaluations ---------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # samples every 100 ms from warm-up to the end of the timed work (all under load)
+    t_w = time.time()
+    for _ in range(args.warmup):
+        ctx.metric_and_gradient(STAGE)
+    while time.time() - t_w < 0.5:  # >= 0.5 s of identical load before timing so the clocks are settled and sampled
+        ctx.metric_and_gradient(STAGE)
+    launches0 = ctx.launch_count()
+    ctx.set_timing(1)
+    ctx.kernel_time_reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            mtot, ninv = ctx.metric_and_gradient(STAGE)
+        e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    kern_ms, kern_launches = ctx.kernel_time_ms("gradient")
+    ctx.set_timing(0)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    total_elems = nel_owned * world
+    value = total_elems / (ms_step * 1e-3) / 1e6  # Melem/s, whole job
+
+    # ---- (2) end to end through the C ABI with pinned host buffers ---------------------------------------------
+    hx = torch.from_numpy(np.ascontiguousarray(X)).pin_memory()
+    hg = torch.empty((3, nnod_local), dtype=torch.float64).pin_memory()
+    hx_np, hg_np = hx.numpy(), hg.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        ctx.upload("coordinates", hx_np)                # H2D 24 B/node
+        m, ni = ctx.metric_and_gradient(STAGE)          # kernels + D2H of {mtot, n_invalid}
+        ctx.download("cg_g", out=hg_np)                 # D2H 24 B/node
+        return m
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_val = total_elems * e2e_steps / float(dt.item()) / 1e6
+
+    # ---- (3) CG iterations/s (device resident; the reference's run_one_iteration incl. line search) ------------
+    cg = {}
+    try:
+        st = ctx.state_init()
+        st.stage = 1
+        ctx.upload("coordinates", X)
+        n_it = 6
+        barrier()
+        t0 = time.perf_counter()
+        for it in range(n_it):
+            st.iter = it
+            st.num_invalid = ctx.count_invalid_elements()
+            gm = ctx.run_one_iteration(st, 0.0)
+        barrier()
+        dtc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(dtc, op=dist.ReduceOp.MAX)
+        cg = {"cg_iters_per_s": n_it / float(dtc.item()), "iters": n_it, "metric_evals": int(st.n_metric_evals),
+              "gradient_evals": int(st.n_gradient_evals), "final_metric": gm, "stage": "ShapeB1"}
+    except pb.SmootherError as ex:  # report, do not hide
+        cg = {"error": str(ex)}
+
+    clocks = sampler.stop()
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the fused metric+gradient evaluation (element pass + deterministic gather) -----------------
+    peak, peak_src = hbm_peak()
+    alg_bytes = ALG_BYTES_PER_NODE_MGRAD * nnod_local + ALG_BYTES_PER_HEX8_CONN * lm.nelems
+    kernel_ms_per_eval = kern_ms / max(args.steps, 1)
+    achieved = alg_bytes / (kernel_ms_per_eval * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("mgrad_dram_bytes_per_eval")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "kernel": "k_elem_pipe<hex8,ShapeB1,grad> + k_grad_gather_csr (one evaluation)",
+                "kernel_ms_per_eval": kernel_ms_per_eval, "algorithmic_bytes_per_eval": alg_bytes,
+                "note": "the evaluation is FP64-pipe-bound (about 1400 FP64 instr/hex vs 64 lanes/clk/SM), see DESIGN.md; "
+                        "fp64 pipe utilisation is in profiles/"}
+
+    # ---- CPU baseline on this box's host cores, bounded sample --------------------------------------------------
+    try:
+        cpu_v, info = cpu_reference(min(n, 128), 12.0)
+        cpu_baseline = {"value": cpu_v / 1e6, "unit": "Melem/s", "cores": info["cores"], "kind": "port",
+                        "sample": f"{info['nele_sample']}^3 hex8 (1/{(n // info['nele_sample']) ** 3} of the workload) x {info['reps']} evaluations, "
+                                  f"{info['seconds']:.1f} s; OpenMP restatement of the reference functors (oracle/liborc_omp.so)"}
+    except Exception as ex:
+        cpu_baseline = {"value": None, "unit": "Melem/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+
+    out = {
+        "metric": "Melem metric+grad evals/s", "value": value, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{n}^3 unstructured hex8 per GPU ({nel_owned} owned elements, {nnod_local} local nodes), unit-cube lattice, "
+                               f"random interior perturbation 0.125h (valid mesh), cube faces fixed, ShapeB1 fused metric+gradient",
+                   "global_cells": [NX, NY, NZ], "partition": f"{px}x{py}x{pz} boxes, 1 ghost layer, owner-computes",
+                   "l2": "inputs (815 MB of coordinates per GPU) exceed the 126 MB L2; no explicit flush"},
+        "e2e": {"value": e2e_val, "unit": "Melem/s", "h2d_bytes_per_step": 24 * nnod_local, "d2h_bytes_per_step": 24 * nnod_local + 16,
+                "steps": e2e_steps, "api": "pms_field_upload(coordinates) + pms_metric_and_gradient + pms_field_download(cg_g), pinned host buffers"},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "cg": cg, "check": {"total_metric": mtot, "n_invalid": int(ninv)}, "setup_s": t_setup,
+    }
+    print(json.dumps(out), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nele", type=int, default=256, help="cells per direction per GPU")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

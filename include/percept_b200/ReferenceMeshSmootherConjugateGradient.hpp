@@ -1,0 +1,453 @@
+// ReferenceMeshSmootherConjugateGradient.hpp — C++ host side of the B200-native smoother.
+//
+// Keeps the reference's smoother class API for this path so that a caller of
+//   percept::ReferenceMeshSmootherConjugateGradientImpl<MeshType>
+//   (src/percept/mesh/mod/smoother/ReferenceMeshSmootherConjugateGradient.hpp:74-174,
+//    ReferenceMeshSmootherBase.hpp:28-105, MeshSmoother.hpp:35-80)
+// can switch to percept_b200::ReferenceMeshSmootherConjugateGradientImpl<MeshType> with the same constructor
+// arguments, the same public/virtual members and the same public state scalars.  All field arithmetic runs in the
+// sm_100a kernels behind the C ABI (percept_smoother_c.h); this header only holds host control flow and converts
+// non-zero statuses into std::runtime_error, the reference's error convention (Util.hpp:288-314).
+//
+// The mesh side is a minimal facade of the pieces of PerceptMesh / BlockStructuredGrid / STK the path touches:
+// fields looked up by name, nodal BLAS-1, the string property map, boundary selectors evaluated once into a fixed
+// mask.  Header-only; link with percept_b200/lib/libpms.so.
+#ifndef PERCEPT_B200_REFERENCE_MESH_SMOOTHER_CG_HPP
+#define PERCEPT_B200_REFERENCE_MESH_SMOOTHER_CG_HPP
+
+#include <array>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../percept_fixtures_c.h"
+#include "../percept_smoother_c.h"
+
+namespace percept_b200 {
+
+typedef double Double;  // MeshType.hpp:41-46 under KOKKOS_ENABLE_CUDA
+
+inline void check(pms_ctx* c, int rc) {
+  if (rc != PMS_OK) throw std::runtime_error(std::string("percept_b200: ") + pms_last_error(c));
+}
+
+typedef std::array<unsigned, 4> StructuredCellIndex;  // i, j, k, block (structured/StructuredCellIndex.hpp)
+
+// ---- structured side -------------------------------------------------------------------------------------------
+struct StructuredBlock {  // structured/StructuredBlock.hpp:31-101 (sizes + boundary conditions + zone connectivity)
+  std::array<unsigned, 3> node_size;
+  struct BC {
+    std::array<int, 3> beg, end;
+  };
+  struct ZoneConnectivity {
+    int donor;
+    std::array<int, 3> transform, owner_beg, owner_end, donor_beg, donor_end;
+  };
+  std::vector<BC> m_boundaryConditions;
+  std::vector<ZoneConnectivity> m_zoneConnectivity;
+  size_t num_nodes() const { return (size_t)node_size[0] * node_size[1] * node_size[2]; }
+};
+
+class PerceptMesh;
+
+class BlockStructuredGrid {  // structured/BlockStructuredGrid.hpp:25-154
+ public:
+  std::vector<std::shared_ptr<StructuredBlock>> m_sblocks;
+  // BlockStructuredGrid::fixture_1 / StructuredBlock::fixture_1 (StructuredBlock.cpp:101-168): one cube block, 6 BCs
+  static std::shared_ptr<BlockStructuredGrid> fixture_1(std::array<unsigned, 3> sizes,
+                                                        std::array<double, 3> widths = {{1, 1, 1}},
+                                                        std::array<double, 3> offsets = {{0, 0, 0}}) {
+    auto bsg = std::make_shared<BlockStructuredGrid>();
+    auto b = std::make_shared<StructuredBlock>();
+    b->node_size = sizes;
+    const int n0 = (int)sizes[0], n1 = (int)sizes[1], n2 = (int)sizes[2];
+    b->m_boundaryConditions = {{{{1, 1, 1}}, {{1, n1, n2}}},   {{{n0, 1, 1}}, {{n0, n1, n2}}}, {{{1, 1, 1}}, {{n0, 1, n2}}},
+                               {{{1, n1, 1}}, {{n0, n1, n2}}}, {{{1, 1, 1}}, {{n0, n1, 1}}},   {{{1, 1, n2}}, {{n0, n1, n2}}}};
+    bsg->m_sblocks.push_back(b);
+    bsg->m_fixture_widths = widths;
+    bsg->m_fixture_offsets = offsets;
+    bsg->m_is_fixture = true;
+    return bsg;
+  }
+  bool m_is_fixture = false;
+  std::array<double, 3> m_fixture_widths{{1, 1, 1}}, m_fixture_offsets{{0, 0, 0}};
+};
+
+struct SGridSelector {  // MeshType.hpp:149-153
+  virtual bool operator()(StructuredCellIndex& index) = 0;
+  virtual ~SGridSelector() {}
+};
+struct SGridMeshGeometry {};  // MeshType.hpp:155-166 (stub in the reference too)
+
+// ---- unstructured (STK) side: the facade takes plain arrays --------------------------------------------------------
+struct STKSelector {  // stands for stk::mesh::Selector evaluated on node buckets: node -> selected?
+  std::function<bool(size_t node)> pred;
+  bool operator()(size_t node) const { return pred(node); }
+};
+class MeshGeometry;  // CAD hooks (classify_node / normal_at / snap): pointer kept in the API, must be null on this path
+
+struct StructuredGrid {
+  typedef SGridSelector MTSelector;
+  typedef SGridMeshGeometry MTMeshGeometry;
+  typedef StructuredCellIndex MTNode;
+  typedef StructuredCellIndex MTElement;
+};
+struct STKMesh {
+  typedef STKSelector MTSelector;
+  typedef MeshGeometry MTMeshGeometry;
+  typedef size_t MTNode;
+  typedef size_t MTElement;
+};
+
+// ---- PerceptMesh facade ----------------------------------------------------------------------------------------
+class PerceptMesh {
+ public:
+  explicit PerceptMesh(int spatial_dim = 3, int device = 0) : m_spatial_dim(spatial_dim) {
+    int rc = pms_create(&m_ctx, device);
+    if (rc != PMS_OK) {
+      std::string msg = m_ctx ? pms_last_error(m_ctx) : "pms_create failed";
+      if (m_ctx) pms_destroy(m_ctx);
+      m_ctx = nullptr;
+      throw std::runtime_error("percept_b200: " + msg);
+    }
+  }
+  ~PerceptMesh() {
+    if (m_ctx) pms_destroy(m_ctx);
+  }
+  PerceptMesh(const PerceptMesh&) = delete;
+  PerceptMesh& operator=(const PerceptMesh&) = delete;
+
+  pms_ctx* ctx() const { return m_ctx; }
+  int get_spatial_dim() const { return m_spatial_dim; }
+  int get_rank() const { return m_rank; }
+  bool get_smooth_surfaces() const { return false; }  // surface smoothing needs CAD queries: out of scope
+
+  // string property map (PerceptMesh.hpp:737-738)
+  void setProperty(const std::string& k, const std::string& v) { m_props[k] = v; }
+  std::string getProperty(const std::string& k) const {
+    auto it = m_props.find(k);
+    return it == m_props.end() ? std::string() : it->second;
+  }
+
+  // structured
+  void set_block_structured_grid(std::shared_ptr<BlockStructuredGrid> bsg) {
+    m_bsg = bsg;
+    for (auto& b : bsg->m_sblocks) {
+      int id = -1;
+      check(m_ctx, pms_add_structured_block(m_ctx, b->node_size.data(), &id));
+      for (auto& bc : b->m_boundaryConditions) check(m_ctx, pms_block_add_boundary_condition(m_ctx, id, bc.beg.data(), bc.end.data()));
+    }
+    for (size_t ib = 0; ib < bsg->m_sblocks.size(); ib++)
+      for (auto& z : bsg->m_sblocks[ib]->m_zoneConnectivity)
+        check(m_ctx, pms_block_add_zone_connectivity(m_ctx, (int)ib, z.donor, z.transform.data(), z.owner_beg.data(),
+                                                     z.owner_end.data(), z.donor_beg.data(), z.donor_end.data()));
+  }
+  std::shared_ptr<BlockStructuredGrid> get_block_structured_grid() const { return m_bsg; }
+  // unstructured (what PerceptMesh::open + STK hand to the smoother): connectivity in Exodus order
+  void set_unstructured_mesh(int topology, size_t nnodes, size_t nelems, const int32_t* conn, const uint8_t* elem_owned = nullptr,
+                             const uint8_t* node_owned = nullptr) {
+    check(m_ctx, pms_set_unstructured(m_ctx, topology, nnodes, nelems, conn, elem_owned, node_owned));
+    m_has_bulk = true;
+  }
+  bool get_bulk_data() const { return m_has_bulk; }
+
+  // add_coordinate_state_fields (PerceptMesh.cpp:4490-4539) = commit: allocates the named fields on the device
+  void add_coordinate_state_fields() {
+    if (!m_committed) check(m_ctx, pms_commit(m_ctx));
+    m_committed = true;
+    if (m_bsg && m_bsg->m_is_fixture) {  // fixture_1 fills "coordinates"
+      auto& b = *m_bsg->m_sblocks[0];
+      std::vector<double> x(3 * b.num_nodes());
+      pms_fixture_cube(b.node_size[0], b.node_size[1], b.node_size[2], m_bsg->m_fixture_widths.data(),
+                       m_bsg->m_fixture_offsets.data(), x.data());
+      set_field("coordinates", x.data(), PMS_SOA, 0);
+    }
+  }
+  bool committed() const { return m_committed; }
+  void set_fixed_mask(const uint8_t* mask) { check(m_ctx, pms_set_fixed_mask(m_ctx, mask)); }
+
+  // field access by name
+  void set_field(const std::string& name, const double* host, int layout = PMS_SOA, int block = -1) {
+    check(m_ctx, pms_field_upload(m_ctx, name.c_str(), block, host, layout));
+  }
+  void get_field(const std::string& name, double* host, int layout = PMS_SOA, int block = -1) const {
+    check(m_ctx, pms_field_download(m_ctx, name.c_str(), block, host, layout));
+  }
+  size_t num_nodes_local() const {
+    size_t n = 0;
+    pms_num_nodes_local(m_ctx, &n);
+    return n;
+  }
+
+  // nodal BLAS-1 (PerceptMesh.hpp:459-536)
+  void copy_field(const std::string& dst, const std::string& src) { check(m_ctx, pms_copy_field(m_ctx, dst.c_str(), src.c_str())); }
+  void nodal_field_axpby(double alpha, const std::string& x, double beta, const std::string& y) {
+    check(m_ctx, pms_nodal_field_axpby(m_ctx, alpha, x.c_str(), beta, y.c_str()));
+  }
+  void nodal_field_axpbypgz(double alpha, const std::string& x, double beta, const std::string& y, double gamma, const std::string& z) {
+    check(m_ctx, pms_nodal_field_axpbypgz(m_ctx, alpha, x.c_str(), beta, y.c_str(), gamma, z.c_str()));
+  }
+  Double nodal_field_dot(const std::string& x, const std::string& y) {
+    double r = 0;
+    check(m_ctx, pms_nodal_field_dot(m_ctx, x.c_str(), y.c_str(), &r));
+    return r;
+  }
+  void nodal_field_set_value(const std::string& x, double v) { check(m_ctx, pms_nodal_field_set_value(m_ctx, x.c_str(), v)); }
+  int get_number_nodes() {
+    size_t n = 0;
+    check(m_ctx, pms_get_number_nodes(m_ctx, &n));
+    return (int)n;
+  }
+
+ private:
+  pms_ctx* m_ctx = nullptr;
+  int m_spatial_dim, m_rank = 0;
+  bool m_committed = false, m_has_bulk = false;
+  std::shared_ptr<BlockStructuredGrid> m_bsg;
+  std::map<std::string, std::string> m_props;
+};
+
+// SGridBoundarySelector (ReferenceMeshSmootherConjugateGradient.hpp:31-69): node in any boundary-condition range
+struct SGridBoundarySelector : public SGridSelector {
+  PerceptMesh* m_eMesh;
+  std::shared_ptr<BlockStructuredGrid> m_bsg;
+  explicit SGridBoundarySelector(PerceptMesh* eMesh) : m_eMesh(eMesh), m_bsg(eMesh->get_block_structured_grid()) {}
+  bool operator()(StructuredCellIndex& index) override {
+    auto& sb = *m_bsg->m_sblocks[index[3]];
+    for (auto& bc : sb.m_boundaryConditions) {
+      bool in = true;
+      for (int d = 0; d < 3; d++) {
+        unsigned beg = (unsigned)std::min(bc.beg[d], bc.end[d]) - 1, end = (unsigned)std::max(bc.beg[d], bc.end[d]) - 1;
+        in = in && beg <= index[d] && index[d] <= end;
+      }
+      if (in) return true;
+    }
+    return false;
+  }
+};
+
+enum { MS_VERTEX, MS_CURVE, MS_SURFACE, MS_VOLUME, MS_ON_BOUNDARY, MS_NOT_ON_BOUNDARY };  // MeshType.hpp:29-38
+
+// ---- smoother class hierarchy ------------------------------------------------------------------------------------
+template <typename MeshType>
+class MeshSmootherImpl {  // MeshSmoother.hpp:35-80
+ protected:
+  PerceptMesh* m_eMesh;
+  int innerIter;
+  double gradNorm;
+  int parallelIterations;
+  STKMesh::MTSelector* m_stk_boundarySelector;
+  StructuredGrid::MTSelector* m_sgrid_boundarySelector;
+
+ public:
+  typename MeshType::MTMeshGeometry* m_meshGeometry;
+
+  MeshSmootherImpl(PerceptMesh* eMesh, STKMesh::MTSelector* stk_select = 0, StructuredGrid::MTSelector* sgrid_select = 0,
+                   typename MeshType::MTMeshGeometry* meshGeometry = 0, int innerIter_ = 100, double gradNorm_ = 1.e-8,
+                   int parallelIterations_ = 20)
+      : m_eMesh(eMesh), innerIter(innerIter_), gradNorm(gradNorm_), parallelIterations(parallelIterations_),
+        m_stk_boundarySelector(stk_select), m_sgrid_boundarySelector(sgrid_select), m_meshGeometry(meshGeometry) {
+    if (meshGeometry)
+      throw std::runtime_error("percept_b200: MeshGeometry (CAD classify/snap) is not data-parallel and is outside this path; pass 0");
+  }
+  virtual ~MeshSmootherImpl() {}
+  StructuredGrid::MTSelector* get_sgrid_select() const { return m_sgrid_boundarySelector; }
+  STKMesh::MTSelector* get_stkmesh_select() const { return m_stk_boundarySelector; }
+
+  static size_t parallel_count_invalid_elements(PerceptMesh* eMesh) {  // MeshSmoother.cpp:192-234
+    size_t n = 0;
+    check(eMesh->ctx(), pms_count_invalid_elements(eMesh->ctx(), &n));
+    return n;
+  }
+  void run() { this->run_algorithm(); }  // MeshSmoother.cpp:420-434
+  virtual void run_algorithm() = 0;
+
+  // get_fixed_flag (MeshSmoother.cpp:271-417) for both mesh types
+  std::pair<bool, int> get_fixed_flag(StructuredCellIndex node) {
+    if (m_sgrid_boundarySelector) {
+      bool f = (*m_sgrid_boundarySelector)(node);
+      return std::make_pair(f, f ? (int)MS_ON_BOUNDARY : (int)MS_NOT_ON_BOUNDARY);
+    }
+    return std::make_pair(false, (int)MS_VOLUME);
+  }
+  std::pair<bool, int> get_fixed_flag(size_t node) {
+    if (m_stk_boundarySelector) {
+      bool f = (*m_stk_boundarySelector)(node);
+      return std::make_pair(f, f ? (int)MS_ON_BOUNDARY : (int)MS_NOT_ON_BOUNDARY);
+    }
+    return std::make_pair(false, (int)MS_VOLUME);
+  }
+
+ protected:
+  // the selectors are evaluated once on the host into the device fixed mask
+  void upload_fixed_mask() {
+    const size_t N = m_eMesh->num_nodes_local();
+    std::vector<uint8_t> mask(N, 0);
+    auto bsg = m_eMesh->get_block_structured_grid();
+    if (bsg) {
+      size_t off = 0;
+      for (unsigned ib = 0; ib < bsg->m_sblocks.size(); ib++) {
+        auto& n = bsg->m_sblocks[ib]->node_size;
+        for (unsigned k = 0; k < n[2]; k++)
+          for (unsigned j = 0; j < n[1]; j++)
+            for (unsigned i = 0; i < n[0]; i++) {
+              StructuredCellIndex idx{{i, j, k, ib}};
+              mask[off + i + (size_t)n[0] * (j + (size_t)n[1] * k)] = get_fixed_flag(idx).first ? 1 : 0;
+            }
+        off += bsg->m_sblocks[ib]->num_nodes();
+      }
+    } else {
+      for (size_t n = 0; n < N; n++) mask[n] = get_fixed_flag(n).first ? 1 : 0;
+    }
+    m_eMesh->set_fixed_mask(mask.data());
+  }
+};
+
+template <typename MeshType>
+class ReferenceMeshSmootherBaseImpl : public MeshSmootherImpl<MeshType> {  // ReferenceMeshSmootherBase.hpp:28-105
+ public:
+  using Base = MeshSmootherImpl<MeshType>;
+  ReferenceMeshSmootherBaseImpl(PerceptMesh* eMesh, STKMesh::MTSelector* stk_select = 0, StructuredGrid::MTSelector* sgrid_select = 0,
+                                typename MeshType::MTMeshGeometry* meshGeometry = 0, int inner_iterations = 100,
+                                double grad_norm = 1.e-8, int parallel_iterations = 20)
+      : Base(eMesh, stk_select, sgrid_select, meshGeometry, inner_iterations, grad_norm, parallel_iterations) {
+    if (eMesh->getProperty("ReferenceMeshSmootherBase_do_anim") != "") m_do_animation = std::stoi(eMesh->getProperty("ReferenceMeshSmootherBase_do_anim"));
+    m_log_name = "smootherlog" + eMesh->getProperty("in_filename") + ".txt";  // ReferenceMeshSmootherBase.cpp:57
+  }
+  virtual ~ReferenceMeshSmootherBaseImpl() {}
+
+ protected:
+  virtual int get_num_stages() { return 2; }
+  virtual double run_one_iteration() { throw std::runtime_error("not implemented"); }
+  virtual bool check_convergence() { throw std::runtime_error("not implemented"); }
+  std::string m_log_name;
+
+ public:
+  double m_scale = 0;
+  Double m_dmax = 0, m_dmax_relative = 0;
+  Double m_dnew = 0, m_dold = 0, m_d0 = 1, m_dmid = 0, m_dd = 0, m_alpha = 0, m_alpha_0 = 0, m_grad_norm = 0, m_grad_norm_scaled = 0;
+  Double m_total_metric = 0;
+  int m_stage = 0, m_iter = 0;
+  size_t m_num_invalid = 0;
+  Double m_global_metric = 1.7976931348623157e308;
+  bool m_untangled = false;
+  size_t m_num_nodes = 0;
+  bool m_use_ref_mesh = true;
+  int m_do_animation = 0;
+};
+
+template <typename MeshType>
+class ReferenceMeshSmootherConjugateGradientImpl : public ReferenceMeshSmootherBaseImpl<MeshType> {
+ public:
+  using Base = ReferenceMeshSmootherBaseImpl<MeshType>;
+  using Base::gradNorm;
+  using Base::innerIter;
+  using Base::m_alpha;
+  using Base::m_alpha_0;
+  using Base::m_d0;
+  using Base::m_dmax;
+  using Base::m_dmax_relative;
+  using Base::m_dmid;
+  using Base::m_dnew;
+  using Base::m_dold;
+  using Base::m_eMesh;
+  using Base::m_global_metric;
+  using Base::m_grad_norm_scaled;
+  using Base::m_iter;
+  using Base::m_num_invalid;
+  using Base::m_num_nodes;
+  using Base::m_stage;
+  using Base::m_total_metric;
+  using Base::m_untangled;
+  using Base::m_use_ref_mesh;
+
+  /// same constructor as the reference (ReferenceMeshSmootherConjugateGradient.hpp:121-128); pointers are borrowed
+  ReferenceMeshSmootherConjugateGradientImpl(PerceptMesh* eMesh, STKMesh::MTSelector* stk_select = 0,
+                                             StructuredGrid::MTSelector* sgrid_select = 0,
+                                             typename MeshType::MTMeshGeometry* meshGeometry = 0, int inner_iterations = 100,
+                                             double grad_norm = 1.e-8, int parallel_iterations = 20)
+      : Base(eMesh, stk_select, sgrid_select, meshGeometry, inner_iterations, grad_norm, parallel_iterations),
+        m_max_edge_length_factor(1.0) {
+    if (!eMesh->committed()) eMesh->add_coordinate_state_fields();
+    this->upload_fixed_mask();
+  }
+  virtual ~ReferenceMeshSmootherConjugateGradientImpl() {}
+
+  double m_max_edge_length_factor;
+
+  virtual void get_gradient() { check(ctx(), pms_get_gradient(ctx(), m_stage)); }  // Def.hpp:1481-1520
+
+  virtual Double total_metric(Double alpha, double /*multiplicative_edge_scaling*/, bool& valid, size_t* num_invalid = 0) {  // Def.hpp:330-388
+    sync_options();
+    double m = 0;
+    size_t n = 0;
+    check(ctx(), pms_total_metric(ctx(), m_stage, alpha, &m, &n));
+    valid = (n == 0);
+    if (num_invalid) *num_invalid = n;
+    return m;
+  }
+  virtual void update_node_positions(Double alpha) {  // Def.hpp:395-410
+    double a = 0, b = 0;
+    check(ctx(), pms_update_node_positions(ctx(), alpha, &a, &b));
+    m_dmax = a;
+    m_dmax_relative = b;
+  }
+  Double get_alpha_0() {  // Def.hpp:906-926
+    double a = 0;
+    check(ctx(), pms_get_alpha_0(ctx(), &a));
+    return a;
+  }
+  void get_edge_lengths(PerceptMesh* /*eMesh*/) { check(ctx(), pms_get_edge_lengths(ctx())); }  // Def.hpp:759-771
+  void get_surface_normals(PerceptMesh*) {}  // only with smooth_surfaces
+  void snap_nodes() {}                       // only with smooth_surfaces
+
+  virtual bool check_convergence() {  // Def.hpp:989-1008
+    pms_state st;
+    to_state(st);
+    return pms_check_convergence(&st, gradNorm) != 0;
+  }
+
+  // line_search + CG step are one C-ABI call; the state scalars are mirrored in and out
+  virtual double run_one_iteration() {  // Def.hpp:1010-1093
+    sync_options();
+    pms_state st;
+    to_state(st);
+    double metric = 0;
+    check(ctx(), pms_run_one_iteration(ctx(), &st, gradNorm, &metric));
+    from_state(st);
+    return metric;
+  }
+
+  virtual void run_algorithm() {  // ReferenceMeshSmootherBase.cpp:240-334 (writes smootherlog<in_filename>.txt)
+    sync_options();
+    pms_state st;
+    int rc = pms_run_algorithm(ctx(), innerIter, gradNorm, this->m_log_name.c_str(), &st);
+    from_state(st);
+    check(ctx(), rc);
+  }
+
+ private:
+  pms_ctx* ctx() const { return m_eMesh->ctx(); }
+  void sync_options() { check(ctx(), pms_set_option(ctx(), "use_ref_mesh", m_use_ref_mesh ? 1.0 : 0.0)); }
+  void to_state(pms_state& st) {
+    st = pms_state();
+    st.dmax = m_dmax; st.dmax_relative = m_dmax_relative; st.dnew = m_dnew; st.dold = m_dold; st.d0 = m_d0; st.dmid = m_dmid;
+    st.alpha = m_alpha; st.alpha_0 = m_alpha_0; st.grad_norm_scaled = m_grad_norm_scaled; st.total_metric = m_total_metric;
+    st.global_metric = m_global_metric; st.stage = m_stage; st.iter = m_iter; st.untangled = m_untangled; st.num_invalid = m_num_invalid;
+    if (m_num_nodes == 0) m_num_nodes = (size_t)m_eMesh->get_number_nodes();
+    st.num_nodes = m_num_nodes;
+  }
+  void from_state(const pms_state& st) {
+    m_dmax = st.dmax; m_dmax_relative = st.dmax_relative; m_dnew = st.dnew; m_dold = st.dold; m_d0 = st.d0; m_dmid = st.dmid;
+    m_alpha = st.alpha; m_alpha_0 = st.alpha_0; m_grad_norm_scaled = st.grad_norm_scaled; m_total_metric = st.total_metric;
+    m_global_metric = st.global_metric; m_stage = st.stage; m_iter = st.iter; m_untangled = st.untangled != 0; m_num_invalid = st.num_invalid;
+    m_num_nodes = st.num_nodes;
+  }
+};
+
+}  // namespace percept_b200
+#endif

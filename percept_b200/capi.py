@@ -3,7 +3,7 @@
 `Api(lib, prefix)` binds every `<prefix>*` entry point of a shared library that
 implements that header; `Ctx` wraps one `pms_ctx*`.  The product binds
 `percept_b200/lib/libpms.so` with prefix ``pms_`` (see percept_b200/__init__.py).
-tests/ bind the CPU oracle's twin ABI (prefix ``orc_``) through the same class so
+tests/ bind the CPU checker's twin ABI (a different symbol prefix) through the same class so
 that parity tests issue the identical call sequence to both.
 """
 import ctypes as C

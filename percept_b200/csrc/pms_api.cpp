@@ -263,7 +263,8 @@ void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t
   for (int b = 0; b < nb; b++) {
     Timed t(c, FAM_METRIC);
     c->L->metric(c->stream, c->dev_blocks[b], stage, c->use_ref_mesh ? 1 : 0, X.d, with_s ? S.d : nullptr, W.d, c->Npad,
-                 alpha, c->R, b, c->keep_elem ? c->d_elem_metric : nullptr, c->keep_elem ? c->d_elem_flag : nullptr);
+                 alpha, c->R, b, c->keep_elem ? c->d_elem_metric : nullptr, c->keep_elem ? c->d_elem_flag : nullptr,
+                 c->d_fixed);
     check_launch(c, "metric");
   }
   fetch(c, 0, nb, nb);
@@ -348,11 +349,8 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv) {
     }
     *mtot = m;
     if (ninv) *ninv = n;
-    // the fused value is the metric at alpha = 0 with the gradient's use_ref flag
-    if (c->cache_metric && use_ref == (c->use_ref_mesh ? 1 : 0)) {
-      if (c->cache.size() >= 8) c->cache.erase(c->cache.begin());
-      c->cache.push_back({X.version, c->field("cg_s").version, W.version, stage, 0.0, m, n, c->use_ref_mesh});
-    }
+    // NOTE: the fused value is not inserted into the metric cache: it equals total_metric(0) only to rounding
+    // (different instruction schedule), and cached values must be bitwise what the metric kernel returns.
   }
 }
 
@@ -385,7 +383,7 @@ double op_alpha0(pms_ctx* c) {
   {
     Timed t(c, FAM_ALPHA0);
     // structured: all nodes (get_alpha_0_refmesh.hpp:168-193); STK: skip fixed nodes (Def.hpp:876-878)
-    c->L->alpha0(c->stream, S.d, EL.d, c->structured ? nullptr : c->d_fixed, c->N, c->Npad, c->R, 0);
+    c->L->alpha0(c->stream, S.d, EL.d, c->structured ? nullptr : c->d_skip, c->N, c->Npad, c->R, 0);
     check_launch(c, "alpha0");
   }
   fetch(c, 0, 1, 0);
@@ -403,7 +401,7 @@ void op_update(pms_ctx* c, double alpha, double* dmax, double* dmax_rel) {
   DField& EL = c->field("cg_edge_length");
   {
     Timed t(c, FAM_UPDATE);
-    c->L->update(c->stream, X.d, LG.d, S.d, EL.d, c->d_fixed, alpha, c->N, c->Npad, c->R, 0);
+    c->L->update(c->stream, X.d, LG.d, S.d, EL.d, c->d_fixed, c->d_node_owned, alpha, c->N, c->Npad, c->R, 0);
     check_launch(c, "update");
   }
   X.version++;
@@ -418,6 +416,13 @@ void op_update(pms_ctx* c, double alpha, double* dmax, double* dmax_rel) {
 uint64_t op_count_invalid(pms_ctx* c) {  // MeshSmoother.cpp:192-234: untangle metric's valid flag
   double m;
   uint64_t n;
+  if (c->cache_metric && !c->keep_elem) {
+    // validity (any corner detA <= 0) is the same rule in both metrics and independent of alpha = 0 evaluations'
+    // stage, so any cached evaluation at the current coordinates already holds the count
+    const uint64_t xv = c->field("coordinates").version;
+    for (auto& e : c->cache)
+      if (e.xv == xv && e.alpha == 0.0) return e.ninv;
+  }
   op_total_metric(c, 0, 0.0, &m, &n);
   return n;
 }
@@ -728,7 +733,7 @@ void pms_destroy(pms_ctx* c) {
     void* ptrs[] = {c->d_conn,      c->d_fixed,     c->d_node_owned, c->d_elem_owned, c->d_dotmask,  c->d_elem_bits,
                     c->d_csr_ptr,   c->d_csr_ent,   c->d_grp_ptr,    c->d_grp_nodes,  c->d_eg,       c->d_elem_metric,
                     c->d_elem_flag, c->R.partial_d, c->R.partial_u,  c->R.ticket,     c->R.out_d,    c->R.out_u,
-                    c->d_send_nodes, c->d_recv_nodes, c->d_send_buf, c->d_recv_buf,   c->d_coll};
+                    c->d_send_nodes, c->d_recv_nodes, c->d_send_buf, c->d_recv_buf,   c->d_coll, c->d_skip};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->h_out_d) cudaFreeHost(c->h_out_d);
@@ -764,6 +769,13 @@ int pms_set_option(pms_ctx* c, const char* key, double v) {
       c->d_elem_metric = dalloc<double>(c->Epad);
       c->d_elem_flag = dalloc<int32_t>(c->Epad);
     }
+  } else if (k == "variant_metric_corners") {
+    c->var_metric = (int)v;
+    pms_fast::set_variant(c->var_metric, c->var_grad);
+    invalidate_cache(c);
+  } else if (k == "variant_grad_corners") {
+    c->var_grad = (int)v;
+    pms_fast::set_variant(c->var_metric, c->var_grad);
   } else
     throw PmsError(PMS_ERR_ARG, "unknown option " + k);
   PMS_CATCH
@@ -831,6 +843,16 @@ int pms_set_unstructured(pms_ctx* c, int topology, size_t nnodes, size_t nelems,
   PMS_CATCH
 }
 
+// nodes skipped by get_alpha_0 on STK meshes: fixed (Def.hpp:876-878) or not owned by this rank
+static void rebuild_skip_mask(pms_ctx* c) {
+  if (c->structured) return;
+  std::vector<uint8_t> skip(c->Npad, 1);
+  for (long long n = 0; n < c->N; n++)
+    skip[n] = (c->h_fixed[n] || (!c->h_node_owned.empty() && !c->h_node_owned[n])) ? 1 : 0;
+  if (!c->d_skip) c->d_skip = dalloc<uint8_t>(c->Npad);
+  PMS_CUDA(cudaMemcpy(c->d_skip, skip.data(), c->Npad, cudaMemcpyHostToDevice));
+}
+
 static long long total_nodes_precommit(pms_ctx* c) {
   if (!c->structured) return c->N;
   long long n = 0;
@@ -848,6 +870,7 @@ int pms_set_fixed_mask(pms_ctx* c, const uint8_t* fixed) {
   c->fixed_set = true;
   if (c->committed) {
     PMS_CUDA(cudaMemcpy(c->d_fixed, c->h_fixed.data(), n, cudaMemcpyHostToDevice));
+    rebuild_skip_mask(c);
     for (auto& mb : c->dev_blocks) c->L->elem_fixed_bits(c->stream, mb, c->d_fixed, c->d_elem_bits);
     check_launch(c, "elem_fixed_bits");
     invalidate_cache(c);
@@ -1083,6 +1106,7 @@ int pms_commit(pms_ctx* c) {
     c->d_elem_flag = dalloc<int32_t>(c->Epad);
   }
   c->committed = true;
+  rebuild_skip_mask(c);
   for (auto& mb : c->dev_blocks) c->L->elem_fixed_bits(c->stream, mb, c->d_fixed, c->d_elem_bits);
   check_launch(c, "elem_fixed_bits");
   PMS_CUDA(cudaStreamSynchronize(c->stream));

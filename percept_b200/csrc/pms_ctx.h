@@ -54,6 +54,7 @@ struct pms_ctx {
   const pmsk::Launchers* L = nullptr;
   bool strict_fp = false, use_ref_mesh = true, cache_metric = true, keep_elem = false, timing = false;
   bool structured = false, committed = false;
+  int var_metric = 2, var_grad = 2;  // kernel variant switches (tuning aid)
 
   // mesh (host description)
   std::vector<HBlock> blocks;
@@ -68,7 +69,8 @@ struct pms_ctx {
   // device mesh
   std::vector<pmsk::MeshDev> dev_blocks;  // one per structured block, or a single entry
   int32_t* d_conn = nullptr;
-  uint8_t *d_fixed = nullptr, *d_node_owned = nullptr, *d_elem_owned = nullptr, *d_dotmask = nullptr, *d_elem_bits = nullptr;
+  uint8_t *d_fixed = nullptr, *d_node_owned = nullptr, *d_elem_owned = nullptr, *d_dotmask = nullptr, *d_elem_bits = nullptr,
+          *d_skip = nullptr;
   int64_t *d_csr_ptr = nullptr, *d_csr_ent = nullptr;
   int64_t *d_grp_ptr = nullptr, *d_grp_nodes = nullptr;
   long long n_groups = 0;

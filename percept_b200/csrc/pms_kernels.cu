@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "pms_device.cuh"
+#include "pms_device_fast.cuh"
 #include "pms_kernels.h"
 
 #ifndef PMS_NS
@@ -23,6 +24,15 @@ namespace PMS_NS {
 
 using namespace pmsk;
 using namespace pmsdev;
+
+#ifdef PMS_STRICT
+constexpr bool STRICT = true;   // reference expression order, -fmad=false: bit-comparable with the CPU oracle
+#else
+constexpr bool STRICT = false;  // flop-reduced hex formulation (pms_device_fast.cuh) + FMA contraction
+#endif
+// hex elements take the flop-reduced path unless strict, or ShapeB1 without a reference mesh (T = A, rare option)
+template <int FL, int STAGE, bool USE_REF>
+__host__ __device__ constexpr bool fast_hex() { return !STRICT && FL != FL_TET4 && (STAGE == 0 || USE_REF); }
 
 constexpr int NT = 256;  // threads per block for all kernels
 constexpr int TBX = 32, TBY = 4, TBZ = 2;  // structured cell tile per block
@@ -56,7 +66,8 @@ __device__ __forceinline__ double block_reduce(double v, double* sm /*[NT/32]*/)
   if ((t & 31) == 0) sm[t >> 5] = v;
   __syncthreads();
   if (t < 32) {
-    v = t < NT / 32 ? sm[t] : OP::id();
+    const int nw = (blockDim.x * blockDim.y * blockDim.z) >> 5;
+    v = t < nw ? sm[t] : OP::id();
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) v = OP::f(v, __shfl_down_sync(0xffffffffu, v, o));
   }
@@ -70,7 +81,8 @@ __device__ __forceinline__ unsigned long long block_reduce_u(unsigned long long 
   if ((t & 31) == 0) sm[t >> 5] = v;
   __syncthreads();
   if (t < 32) {
-    v = t < NT / 32 ? sm[t] : 0ull;
+    const int nw = (blockDim.x * blockDim.y * blockDim.z) >> 5;
+    v = t < nw ? sm[t] : 0ull;
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   }
@@ -105,13 +117,14 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], unsigned long long 
 #pragma unroll
   for (int k = 0; k < NV; k++) {
     double a = OP::id();
-    for (unsigned i = t; i < nb; i += NT) a = OP::f(a, __ldcg(&R.partial_d[(size_t)k * R.max_blocks + i]));
+    for (unsigned i = t; i < nb; i += blockDim.x * blockDim.y * blockDim.z)
+      a = OP::f(a, __ldcg(&R.partial_d[(size_t)k * R.max_blocks + i]));
     a = block_reduce<OP>(a, smd);
     if (t == 0) R.out_d[slot + k] = a;
   }
   if (WITH_U) {
     unsigned long long a = 0;
-    for (unsigned i = t; i < nb; i += NT) a += __ldcg(&R.partial_u[i]);
+    for (unsigned i = t; i < nb; i += blockDim.x * blockDim.y * blockDim.z) a += __ldcg(&R.partial_u[i]);
     a = block_reduce_u(a, smu);
     if (t == 0) R.out_u[slot] = a;
   }
@@ -121,10 +134,22 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], unsigned long long 
 // ------------------------------------------------------------------------------------------------
 // element addressing
 // ------------------------------------------------------------------------------------------------
+// Work is cut into tiles of NT elements (structured: TBX x TBY x TBZ cells); blocks are persistent and stride over
+// the tiles, so each thread accumulates many elements and the block reduces once at the end.
 template <int FL>
-__device__ __forceinline__ bool element_of_thread(const MeshDev& m, long long& e, long long (&nid)[8]) {
+__host__ __device__ inline long long num_tiles(const MeshDev& m) {
+  if (FL == FL_SGRID)
+    return (long long)((m.ni - 1 + TBX - 1) / TBX) * ((m.nj - 1 + TBY - 1) / TBY) * ((m.nk - 1 + TBZ - 1) / TBZ);
+  return (m.nelems + NT - 1) / NT;
+}
+
+template <int FL>
+__device__ __forceinline__ bool element_of_tile(const MeshDev& m, const long long tile, long long& e, long long (&nid)[8]) {
   if (FL == FL_SGRID) {
-    const int i = blockIdx.x * TBX + threadIdx.x, j = blockIdx.y * TBY + threadIdx.y, k = blockIdx.z * TBZ + threadIdx.z;
+    const int nbx = (m.ni - 1 + TBX - 1) / TBX, nby = (m.nj - 1 + TBY - 1) / TBY;
+    const int bx = (int)(tile % nbx), by = (int)((tile / nbx) % nby), bz = (int)(tile / ((long long)nbx * nby));
+    const int t = threadIdx.x;
+    const int i = bx * TBX + (t & (TBX - 1)), j = by * TBY + ((t / TBX) & (TBY - 1)), k = bz * TBZ + t / (TBX * TBY);
     const int nci = m.ni - 1, ncj = m.nj - 1, nck = m.nk - 1;
     if (i >= nci || j >= ncj || k >= nck) return false;
     e = i + (long long)nci * (j + (long long)ncj * k);
@@ -134,7 +159,7 @@ __device__ __forceinline__ bool element_of_thread(const MeshDev& m, long long& e
     for (int a = 0; a < 8; a++) nid[a] = n0 + (a & 1) + ((a >> 1) & 1) * sj + (a >> 2) * sk;  // total_element_metric.cpp:286-302
     return true;
   } else {
-    e = (long long)blockIdx.x * NT + threadIdx.x;
+    e = tile * NT + threadIdx.x;
     if (e >= m.nelems) return false;
     constexpr int NN = npe<FL>();
 #pragma unroll
@@ -143,14 +168,344 @@ __device__ __forceinline__ bool element_of_thread(const MeshDev& m, long long& e
   }
 }
 
+constexpr int PERSIST_BLOCKS = 148 * 8;  // 148 SMs x up to 8 CTAs; tiles beyond that are strided
 template <int FL>
-static dim3 elem_grid(const MeshDev& m, dim3& block) {
-  if (FL == FL_SGRID) {
-    block = dim3(TBX, TBY, TBZ);
-    return dim3((m.ni - 1 + TBX - 1) / TBX, (m.nj - 1 + TBY - 1) / TBY, (m.nk - 1 + TBZ - 1) / TBZ);
+static unsigned elem_grid(const MeshDev& m) {
+  const long long nt = num_tiles<FL>(m);
+  return (unsigned)(nt < PERSIST_BLOCKS ? (nt < 1 ? 1 : nt) : PERSIST_BLOCKS);
+}
+
+// position of local vertex a in the register array: Exodus hex8 order is permuted to structured numbering on the
+// flop-reduced path (same corner set, BlockStructuredGrid.cpp:20)
+template <int FL, bool FAST>
+__device__ __forceinline__ constexpr int vpos(int a) { return (FAST && FL == FL_HEX8) ? hex_perm(a) : a; }
+
+// ------------------------------------------------------------------------------------------------
+// Corner-parallel hex kernels (default build): 8 lanes per hex, lane c evaluates the corner Jacobian at local node c
+// (structured numbering), neighbour vertices and gradient columns travel by warp shuffle (xor 1,2,4).  ~60-100
+// registers per thread instead of ~250, so several CTAs per SM keep the FP64 pipe fed.  A CTA handles 32 hexes at a
+// time (4 per warp).  Structured blocks: a CTA owns an 8 x 4 column of cells and marches a chunk of k-layers, so the
+// per-hex index arithmetic is one pointer increment.
+//
+// Edges are taken "neighbour minus self" (e_s = v[c^(1<<s)] - v[c]); versus the canonical +axis orientation this flips
+// the columns s with bit s of c set, in A and W alike: T = A W^-1 and y are unchanged, both determinants pick up
+// p = (-1)^popc(c), and d(mu)/d(e_s) comes out directly in the flipped frame (see pms_device_fast.cuh).
+// ------------------------------------------------------------------------------------------------
+constexpr int CT_I = 8, CT_J = 4;   // structured tile: 8 x 4 cells per k-layer
+constexpr int CT_KCHUNK = 64;       // k-layers marched by one CTA
+
+__device__ __forceinline__ double shfl_xor_d(double v, int lanemask) { return __shfl_xor_sync(0xffffffffu, v, lanemask); }
+
+// One hex corner per lane.  Accumulates the metric into val/inv, writes the per-element gradient to eg.
+template <int FL, int STAGE, bool GRAD, bool WITH_S>
+__device__ __forceinline__ void corner_body(const MeshDev& m, const bool active, const long long e, const long long node,
+                                            const int lane, const int c, const double* __restrict__ x,
+                                            const double* __restrict__ s, const double* __restrict__ w,
+                                            const long long stride, const double alpha, double* __restrict__ eg,
+                                            const long long eg_stride, const uint8_t* __restrict__ fixed,
+                                            double* __restrict__ em, int32_t* __restrict__ ef, double& val,
+                                            unsigned long long& inv) {
+  double xc[3] = {0.0, 0.0, 0.0}, wc[3] = {0.0, 0.0, 0.0};
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      double xv = __ldg(&x[r * stride + node]);
+      if (WITH_S) {
+        if (!fixed[node]) xv += alpha * __ldg(&s[r * stride + node]);  // update_coordinates.cpp:255-256
+      }
+      xc[r] = xv;
+      wc[r] = __ldg(&w[r * stride + node]);
+    }
   }
-  block = dim3(NT, 1, 1);
-  return dim3((unsigned)((m.nelems + NT - 1) / NT), 1, 1);
+  double a[3][3], ww[3][3];
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      a[ax][r] = shfl_xor_d(xc[r], 1 << ax) - xc[r];
+      ww[ax][r] = shfl_xor_d(wc[r], 1 << ax) - wc[r];
+    }
+  const double p = (__popc(c) & 1) ? -1.0 : 1.0;
+  double detA, dM[3][3];
+  bool have;
+  const double mm = hex_corner_fast<STAGE, GRAD>(a[0], a[1], a[2], ww[0], ww[1], ww[2], p, detA, dM, have);
+  const unsigned bal = __ballot_sync(0xffffffffu, detA > 0.0);
+  const bool valid = ((bal >> (lane & 24)) & 0xffu) == 0xffu;  // all 8 corners of this hex
+  bool counted = active;
+  if (FL != FL_SGRID && m.elem_owned && active) counted = m.elem_owned[e] != 0;
+  if (counted) {
+    val += mm;
+    if (c == 0) inv += valid ? 0 : 1;
+  }
+  if (em) {  // per-element outputs (debug/parity aid): sum the 8 corner terms of the hex
+    double t = mm;
+    t += shfl_xor_d(t, 1);
+    t += shfl_xor_d(t, 2);
+    t += shfl_xor_d(t, 4);
+    if (active && c == 0) {
+      em[m.elem_off + e] = counted ? t : 0.0;
+      if (ef) ef[m.elem_off + e] = counted ? (valid ? 0 : 1) : 0;
+    }
+  }
+  if (GRAD) {
+    const bool use = have && (valid || STAGE == 0);  // gradient_functors.hpp:391, Def.hpp:1219
+    double g[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const double mine = use ? dM[r][ax] : 0.0;
+        g[r] += shfl_xor_d(mine, 1 << ax) - mine;  // +column from the neighbour's corner, -column of my own
+      }
+    if (active) {
+      const int a_out = (FL == FL_HEX8) ? (c ^ ((c >> 1) & 1)) : c;  // structured corner -> Exodus local node
+      const long long ge = m.elem_off + e;
+#pragma unroll
+      for (int r = 0; r < 3; r++) eg[(long long)(a_out * 3 + r) * eg_stride + ge] = g[r];
+    }
+  }
+}
+
+template <int FL, int STAGE, bool GRAD, bool WITH_S>
+__global__ void __launch_bounds__(NT) k_corners(const MeshDev m, const double* __restrict__ x, const double* __restrict__ s,
+                                                const double* __restrict__ w, const long long stride, const double alpha,
+                                                double* __restrict__ eg, const long long eg_stride,
+                                                const uint8_t* __restrict__ fixed, const Reduce R, const int slot,
+                                                double* __restrict__ em, int32_t* __restrict__ ef) {
+  const int lane = threadIdx.x & 31, c = lane & 7, warp = threadIdx.x >> 5, el = lane >> 3;
+  double val[1] = {0.0};
+  unsigned long long inv = 0;
+  if (FL == FL_SGRID) {
+    const int nci = m.ni - 1, ncj = m.nj - 1, nck = m.nk - 1;
+    const int nbx = (nci + CT_I - 1) / CT_I;
+    const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
+    const int i = bx * CT_I + (warp & 1) * 4 + el, j = by * CT_J + (warp >> 1);
+    const bool active = i < nci && j < ncj;
+    const int k0 = blockIdx.y * CT_KCHUNK, k1 = min(k0 + CT_KCHUNK, nck);
+    const long long sk = (long long)m.ni * m.nj, se = (long long)nci * ncj;
+    long long node = m.node_off + (i + (c & 1)) + (long long)m.ni * (j + ((c >> 1) & 1)) + sk * (k0 + (c >> 2));
+    long long e = i + (long long)nci * j + se * k0;
+    for (int k = k0; k < k1; k++, node += sk, e += se)
+      corner_body<FL, STAGE, GRAD, WITH_S>(m, active, e, node, lane, c, x, s, w, stride, alpha, eg, eg_stride, fixed, em, ef,
+                                           val[0], inv);
+  } else {
+    const long long ntiles = (m.nelems + 31) / 32;
+    const int a = c ^ ((c >> 1) & 1);  // Exodus local node of structured corner c (swap 2<->3, 6<->7)
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long e = tile * 32 + warp * 4 + el;
+      const bool active = e < m.nelems;
+      long long node = 0;
+      if (active) node = __ldg(&m.conn[(long long)a * m.conn_stride + e]);
+      corner_body<FL, STAGE, GRAD, WITH_S>(m, active, e, node, lane, c, x, s, w, stride, alpha, eg, eg_stride, fixed, em, ef,
+                                           val[0], inv);
+    }
+  }
+  grid_reduce<OpSum, 1, true>(val, inv, R, slot);
+}
+
+template <int FL>
+static dim3 corner_grid(const MeshDev& m) {
+  if (FL == FL_SGRID)
+    return dim3((unsigned)(((m.ni - 1 + CT_I - 1) / CT_I) * ((m.nj - 1 + CT_J - 1) / CT_J)),
+                (unsigned)((m.nk - 1 + CT_KCHUNK - 1) / CT_KCHUNK), 1);
+  const long long nt = (m.nelems + 31) / 32;
+  const long long cap = 148LL * 16;
+  return dim3((unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), 1, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Software-pipelined element kernel (default build, all element kinds): one element per thread, persistent CTAs of
+// NTP threads.  While a thread evaluates element t, the vertex data of its next element (x, [s], w for 8 or 4 nodes)
+// is already in flight: cp.async (LDGSTS) gathers it into a THREAD-PRIVATE column of shared memory
+// sm[value][thread] (bank-conflict free, no __syncthreads), and connectivity is fetched one element further ahead.
+// Memory latency is thus hidden behind ~2k instructions of FP64 work instead of by occupancy, which the ~170-250
+// registers per thread of the hex metric do not allow.
+// ------------------------------------------------------------------------------------------------
+constexpr int NTP = 128;
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int FL>
+__host__ __device__ inline long long num_ptiles(const MeshDev& m) {
+  if (FL == FL_SGRID) return (long long)((m.ni - 1 + 31) / 32) * ((m.nj - 1 + 3) / 4) * (m.nk - 1);
+  return (m.nelems + NTP - 1) / NTP;
+}
+
+// element of this thread in pipelined tile `tile` (structured tile: 32 x 4 cells of one k-layer); structured node ids
+template <int FL>
+__device__ __forceinline__ bool ptile_element(const MeshDev& m, const long long tile, long long& e, long long& n0) {
+  if (FL == FL_SGRID) {
+    const int nci = m.ni - 1, ncj = m.nj - 1;
+    const int nbx = (nci + 31) / 32, nby = (ncj + 3) / 4;
+    const int bx = (int)(tile % nbx);
+    const long long rest = tile / nbx;
+    const int by = (int)(rest % nby), k = (int)(rest / nby);
+    const int i = bx * 32 + (threadIdx.x & 31), j = by * 4 + (threadIdx.x >> 5);
+    if (i >= nci || j >= ncj) return false;
+    e = i + (long long)nci * (j + (long long)ncj * k);
+    n0 = m.node_off + i + (long long)m.ni * (j + (long long)m.nj * k);
+    return true;
+  } else {
+    e = tile * NTP + threadIdx.x;
+    n0 = 0;
+    return e < m.nelems;
+  }
+}
+
+#ifndef PIPE_MINB_METRIC
+#define PIPE_MINB_METRIC 2
+#endif
+#ifndef PIPE_MINB_GRAD
+#define PIPE_MINB_GRAD 2
+#endif
+template <int FL, int STAGE, bool USE_REF, bool GRAD, bool WITH_S>
+__global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC)) k_elem_pipe(const MeshDev m, const double* __restrict__ x,
+                                                   const double* __restrict__ s, const double* __restrict__ w,
+                                                   const long long stride, const double alpha, double* __restrict__ eg,
+                                                   const long long eg_stride, const Reduce R, const int slot,
+                                                   double* __restrict__ em, int32_t* __restrict__ ef) {
+  constexpr bool FAST = fast_hex<FL, STAGE, USE_REF>();
+  constexpr int NN = npe<FL>();
+  extern __shared__ double sm[];  // [NN*3*(WITH_S ? 3 : 2)][NTP]
+  const int tid = threadIdx.x;
+  double* my = sm + tid;
+  auto slot_of = [&](int arr, int a, int r) -> double* { return my + ((arr * NN + a) * 3 + r) * NTP; };
+
+  double val[1] = {0.0};
+  unsigned long long inv = 0;
+  const long long ntiles = num_ptiles<FL>(m);
+
+  // --- pipeline state: element being computed (cur), element whose vertex data is in flight (nxt),
+  //     element whose connectivity is in flight (unstructured only: nn_*)
+  long long e_cur = 0, e_nxt = 0, n0 = 0;
+  bool act_cur = false, act_nxt = false;
+  unsigned bits_cur = 0, bits_nxt = 0;
+  int conn_nn[8];
+  bool act_nn = false;
+  long long e_nn = 0;
+
+  auto load_conn = [&](long long tile) {  // connectivity of the element after next
+    act_nn = false;
+    if (tile < ntiles) {
+      long long dummy;
+      act_nn = ptile_element<FL>(m, tile, e_nn, dummy);
+      if (act_nn) {
+#pragma unroll
+        for (int a = 0; a < NN; a++) conn_nn[a] = __ldg(&m.conn[(long long)a * m.conn_stride + e_nn]);
+      }
+    }
+  };
+  auto issue = [&](long long tile) {  // start the gather of the next element's vertex data
+    act_nxt = false;
+    if (FL == FL_SGRID) {
+      if (tile < ntiles) act_nxt = ptile_element<FL>(m, tile, e_nxt, n0);
+    } else {
+      act_nxt = act_nn;
+      e_nxt = e_nn;
+    }
+    if (act_nxt) {
+      const long long sj = m.ni, sk = (long long)m.ni * m.nj;
+#pragma unroll
+      for (int a = 0; a < NN; a++) {
+        long long nid;
+        if (FL == FL_SGRID)
+          nid = n0 + (a & 1) + ((a >> 1) & 1) * sj + (a >> 2) * sk;  // total_element_metric.cpp:286-302
+        else
+          nid = conn_nn[a];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          cp_async8(slot_of(0, a, r), &x[r * stride + nid]);
+          cp_async8(slot_of(1, a, r), &w[r * stride + nid]);
+          if (WITH_S) cp_async8(slot_of(2, a, r), &s[r * stride + nid]);
+        }
+      }
+      if (WITH_S) bits_nxt = m.elem_fixed_bits[m.elem_off + e_nxt];
+    }
+    cp_async_commit();
+  };
+
+  long long tile = blockIdx.x;
+  if (FL != FL_SGRID) load_conn(tile);
+  issue(tile);
+  if (FL != FL_SGRID) load_conn(tile + gridDim.x);
+
+  for (; tile < ntiles; tile += gridDim.x) {
+    e_cur = e_nxt;
+    act_cur = act_nxt;
+    bits_cur = bits_nxt;
+    cp_async_wait_all();
+    double vc[8][3], vo[8][3];
+    if (act_cur) {
+#pragma unroll
+      for (int a = 0; a < NN; a++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          double xv = *slot_of(0, a, r);
+          if (WITH_S) {
+            if (!((bits_cur >> a) & 1u)) xv += alpha * *slot_of(2, a, r);  // update_coordinates.cpp:255-256
+          }
+          vc[vpos<FL, FAST>(a)][r] = xv;
+          vo[vpos<FL, FAST>(a)][r] = *slot_of(1, a, r);
+        }
+    }
+    // the values above are in registers before the slots are re-armed (same-thread program order on the LSU)
+    asm volatile("" ::: "memory");
+    issue(tile + gridDim.x);
+    if (FL != FL_SGRID) load_conn(tile + 2 * (long long)gridDim.x);
+    if (!act_cur) continue;
+
+    bool valid;
+    double mm;
+    double grad[8][3];
+    if (FAST) {
+      mm = hex_metric_fast<STAGE, GRAD>(vc, vo, valid, grad);
+    } else if (GRAD) {
+      mm = element_grad_metric<FL, STAGE, USE_REF>(vc, vo, valid, grad);
+    } else {
+      mm = element_metric<FL, STAGE, USE_REF>(vc, vo, valid);
+    }
+    const long long ge = m.elem_off + e_cur;
+    if (GRAD) {
+      const bool use = valid || STAGE == 0;  // gradient_functors.hpp:391, Def.hpp:1219
+#pragma unroll
+      for (int a = 0; a < NN; a++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) eg[(long long)(a * 3 + r) * eg_stride + ge] = use ? grad[vpos<FL, FAST>(a)][r] : 0.0;
+    }
+    bool counted = true;
+    if (FL != FL_SGRID && m.elem_owned) counted = m.elem_owned[e_cur] != 0;
+    if (counted) {
+      val[0] += mm;
+      inv += valid ? 0 : 1;
+    }
+    if (em) em[ge] = counted ? mm : 0.0;
+    if (ef) ef[ge] = counted ? (valid ? 0 : 1) : 0;
+  }
+  grid_reduce<OpSum, 1, true>(val, inv, R, slot);
+}
+
+template <int FL, int STAGE, bool USE_REF, bool GRAD, bool WITH_S>
+static void launch_elem_pipe(cudaStream_t st, const MeshDev& m, const double* x, const double* s, const double* w,
+                             long long stride, double alpha, double* eg, long long egs, const Reduce& R, int slot,
+                             double* em, int32_t* ef) {
+  constexpr int NV = npe<FL>() * 3 * (WITH_S ? 3 : 2);
+  const size_t smem = (size_t)NV * NTP * sizeof(double);
+  auto kern = k_elem_pipe<FL, STAGE, USE_REF, GRAD, WITH_S>;
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NTP, smem);
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  const long long nt = num_ptiles<FL>(m);
+  const long long cap = 148LL * blocks_per_sm;
+  const unsigned grid = (unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap);
+  kern<<<grid, NTP, smem, st>>>(m, x, s, w, stride, alpha, eg, egs, R, slot, em, ef);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -161,11 +516,14 @@ __global__ void __launch_bounds__(NT) k_metric(const MeshDev m, const double* __
                                                const double* __restrict__ w, const long long stride, const double alpha,
                                                const Reduce R, const int slot, double* __restrict__ em,
                                                int32_t* __restrict__ ef) {
-  long long e, nid[8];
+  constexpr bool FAST = fast_hex<FL, STAGE, USE_REF>();
+  constexpr int NN = npe<FL>();
   double val[1] = {0.0};
   unsigned long long inv = 0;
-  if (element_of_thread<FL>(m, e, nid)) {
-    constexpr int NN = npe<FL>();
+  const long long ntiles = num_tiles<FL>(m);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long e, nid[8];
+    if (!element_of_tile<FL>(m, tile, e, nid)) continue;
     double vc[8][3], vo[8][3];
     unsigned bits = 0;
     if (WITH_S) bits = m.elem_fixed_bits[m.elem_off + e];
@@ -180,16 +538,22 @@ __global__ void __launch_bounds__(NT) k_metric(const MeshDev m, const double* __
             xv += dt;
           }
         }
-        vc[a][r] = xv;
-        vo[a][r] = __ldg(&w[r * stride + nid[a]]);
+        vc[vpos<FL, FAST>(a)][r] = xv;
+        vo[vpos<FL, FAST>(a)][r] = __ldg(&w[r * stride + nid[a]]);
       }
     bool valid;
-    double mm = element_metric<FL, STAGE, USE_REF>(vc, vo, valid);
+    double mm;
+    if (FAST) {
+      double dummy[8][3];
+      mm = hex_metric_fast<STAGE, false>(vc, vo, valid, dummy);
+    } else {
+      mm = element_metric<FL, STAGE, USE_REF>(vc, vo, valid);
+    }
     bool counted = true;
     if (FL != FL_SGRID && m.elem_owned) counted = m.elem_owned[e] != 0;
     if (counted) {
-      val[0] = mm;
-      inv = valid ? 0 : 1;
+      val[0] += mm;
+      inv += valid ? 0 : 1;
     }
     if (em) em[m.elem_off + e] = counted ? mm : 0.0;
     if (ef) ef[m.elem_off + e] = counted ? (valid ? 0 : 1) : 0;
@@ -197,35 +561,53 @@ __global__ void __launch_bounds__(NT) k_metric(const MeshDev m, const double* __
   grid_reduce<OpSum, 1, true>(val, inv, R, slot);
 }
 
+int g_metric_corners = 2;  // default-build metric kernel: 2 = pipelined element kernel, 1 = corner-parallel hex, 0 = simple
 template <int FL, int STAGE, bool USE_REF>
 static void launch_metric2(cudaStream_t st, const MeshDev& m, const double* x, const double* s, const double* w,
-                           long long stride, double alpha, const Reduce& R, int slot, double* em, int32_t* ef) {
-  dim3 block, grid = elem_grid<FL>(m, block);
+                           long long stride, double alpha, const Reduce& R, int slot, double* em, int32_t* ef,
+                           const uint8_t* fixed) {
+  if (!STRICT && g_metric_corners == 2) {
+    if (s && alpha != 0.0)
+      launch_elem_pipe<FL, STAGE, USE_REF, false, true>(st, m, x, s, w, stride, alpha, nullptr, 0, R, slot, em, ef);
+    else
+      launch_elem_pipe<FL, STAGE, USE_REF, false, false>(st, m, x, s, w, stride, alpha, nullptr, 0, R, slot, em, ef);
+    return;
+  }
+  if (fast_hex<FL, STAGE, USE_REF>() && g_metric_corners == 1 && FL != FL_TET4) {
+    constexpr int F2 = FL == FL_TET4 ? FL_HEX8 : FL;
+    const dim3 cg = corner_grid<F2>(m);
+    if (s && alpha != 0.0)
+      k_corners<F2, STAGE, false, true><<<cg, NT, 0, st>>>(m, x, s, w, stride, alpha, nullptr, 0, fixed, R, slot, em, ef);
+    else
+      k_corners<F2, STAGE, false, false><<<cg, NT, 0, st>>>(m, x, s, w, stride, alpha, nullptr, 0, fixed, R, slot, em, ef);
+    return;
+  }
+  const unsigned grid = elem_grid<FL>(m);
   if (s && alpha != 0.0)
-    k_metric<FL, STAGE, USE_REF, true><<<grid, block, 0, st>>>(m, x, s, w, stride, alpha, R, slot, em, ef);
+    k_metric<FL, STAGE, USE_REF, true><<<grid, NT, 0, st>>>(m, x, s, w, stride, alpha, R, slot, em, ef);
   else
-    k_metric<FL, STAGE, USE_REF, false><<<grid, block, 0, st>>>(m, x, s, w, stride, alpha, R, slot, em, ef);
+    k_metric<FL, STAGE, USE_REF, false><<<grid, NT, 0, st>>>(m, x, s, w, stride, alpha, R, slot, em, ef);
 }
 template <int FL>
 static void launch_metric1(cudaStream_t st, const MeshDev& m, int stage, int use_ref, const double* x, const double* s,
                            const double* w, long long stride, double alpha, const Reduce& R, int slot, double* em,
-                           int32_t* ef) {
+                           int32_t* ef, const uint8_t* fixed) {
   if (stage == 0)
-    launch_metric2<FL, 0, true>(st, m, x, s, w, stride, alpha, R, slot, em, ef);
+    launch_metric2<FL, 0, true>(st, m, x, s, w, stride, alpha, R, slot, em, ef, fixed);
   else if (use_ref)
-    launch_metric2<FL, 1, true>(st, m, x, s, w, stride, alpha, R, slot, em, ef);
+    launch_metric2<FL, 1, true>(st, m, x, s, w, stride, alpha, R, slot, em, ef, fixed);
   else
-    launch_metric2<FL, 1, false>(st, m, x, s, w, stride, alpha, R, slot, em, ef);
+    launch_metric2<FL, 1, false>(st, m, x, s, w, stride, alpha, R, slot, em, ef, fixed);
 }
 static void launch_metric(cudaStream_t st, const MeshDev& m, int stage, int use_ref, const double* x, const double* s,
                           const double* w, long long stride, double alpha, const Reduce& R, int slot, double* em,
-                          int32_t* ef) {
+                          int32_t* ef, const uint8_t* fixed) {
   if (m.kind == KIND_SGRID)
-    launch_metric1<FL_SGRID>(st, m, stage, use_ref, x, s, w, stride, alpha, R, slot, em, ef);
+    launch_metric1<FL_SGRID>(st, m, stage, use_ref, x, s, w, stride, alpha, R, slot, em, ef, fixed);
   else if (m.kind == KIND_HEX8)
-    launch_metric1<FL_HEX8>(st, m, stage, use_ref, x, s, w, stride, alpha, R, slot, em, ef);
+    launch_metric1<FL_HEX8>(st, m, stage, use_ref, x, s, w, stride, alpha, R, slot, em, ef, fixed);
   else
-    launch_metric1<FL_TET4>(st, m, stage, use_ref, x, s, w, stride, alpha, R, slot, em, ef);
+    launch_metric1<FL_TET4>(st, m, stage, use_ref, x, s, w, stride, alpha, R, slot, em, ef, fixed);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -237,32 +619,39 @@ __global__ void __launch_bounds__(NT) k_grad_elements(const MeshDev m, const dou
                                                       const double* __restrict__ w, const long long stride,
                                                       double* __restrict__ eg, const long long eg_stride, const Reduce R,
                                                       const int slot, double* __restrict__ em, int32_t* __restrict__ ef) {
-  long long e, nid[8];
+  constexpr bool FAST = fast_hex<FL, STAGE, USE_REF>();
+  constexpr int NN = npe<FL>();
   double val[1] = {0.0};
   unsigned long long inv = 0;
-  if (element_of_thread<FL>(m, e, nid)) {
-    constexpr int NN = npe<FL>();
+  const long long ntiles = num_tiles<FL>(m);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long e, nid[8];
+    if (!element_of_tile<FL>(m, tile, e, nid)) continue;
     double vc[8][3], vo[8][3], grad[8][3];
 #pragma unroll
     for (int a = 0; a < NN; a++)
 #pragma unroll
       for (int r = 0; r < 3; r++) {
-        vc[a][r] = __ldg(&x[r * stride + nid[a]]);
-        vo[a][r] = __ldg(&w[r * stride + nid[a]]);
+        vc[vpos<FL, FAST>(a)][r] = __ldg(&x[r * stride + nid[a]]);
+        vo[vpos<FL, FAST>(a)][r] = __ldg(&w[r * stride + nid[a]]);
       }
     bool valid;
-    double mm = element_grad_metric<FL, STAGE, USE_REF>(vc, vo, valid, grad);
+    double mm;
+    if (FAST)
+      mm = hex_metric_fast<STAGE, true>(vc, vo, valid, grad);
+    else
+      mm = element_grad_metric<FL, STAGE, USE_REF>(vc, vo, valid, grad);
     const bool use = valid || STAGE == 0;  // gradient_functors.hpp:391, Def.hpp:1219
     const long long ge = m.elem_off + e;
 #pragma unroll
     for (int a = 0; a < NN; a++)
 #pragma unroll
-      for (int r = 0; r < 3; r++) eg[(long long)(a * 3 + r) * eg_stride + ge] = use ? grad[a][r] : 0.0;
+      for (int r = 0; r < 3; r++) eg[(long long)(a * 3 + r) * eg_stride + ge] = use ? grad[vpos<FL, FAST>(a)][r] : 0.0;
     bool counted = true;
     if (FL != FL_SGRID && m.elem_owned) counted = m.elem_owned[e] != 0;
     if (counted) {
-      val[0] = mm;
-      inv = valid ? 0 : 1;
+      val[0] += mm;
+      inv += valid ? 0 : 1;
     }
     if (em) em[ge] = counted ? mm : 0.0;
     if (ef) ef[ge] = counted ? (valid ? 0 : 1) : 0;
@@ -270,17 +659,36 @@ __global__ void __launch_bounds__(NT) k_grad_elements(const MeshDev m, const dou
   grid_reduce<OpSum, 1, true>(val, inv, R, slot);
 }
 
+int g_grad_corners = 2;  // default-build gradient element pass: 2 = pipelined, 1 = corner-parallel hex, 0 = simple
 template <int FL>
 static void launch_grad_elements1(cudaStream_t st, const MeshDev& m, int stage, int use_ref, const double* x,
                                   const double* w, long long stride, double* eg, long long egs, const Reduce& R, int slot,
                                   double* em, int32_t* ef) {
-  dim3 block, grid = elem_grid<FL>(m, block);
+  if (!STRICT && g_grad_corners == 2) {
+    if (stage == 0)
+      launch_elem_pipe<FL, 0, true, true, false>(st, m, x, nullptr, w, stride, 0.0, eg, egs, R, slot, em, ef);
+    else if (use_ref)
+      launch_elem_pipe<FL, 1, true, true, false>(st, m, x, nullptr, w, stride, 0.0, eg, egs, R, slot, em, ef);
+    else
+      launch_elem_pipe<FL, 1, false, true, false>(st, m, x, nullptr, w, stride, 0.0, eg, egs, R, slot, em, ef);
+    return;
+  }
+  if (!STRICT && FL != FL_TET4 && g_grad_corners == 1 && (stage == 0 || use_ref)) {
+    constexpr int F2 = FL == FL_TET4 ? FL_HEX8 : FL;
+    const dim3 cg = corner_grid<F2>(m);
+    if (stage == 0)
+      k_corners<F2, 0, true, false><<<cg, NT, 0, st>>>(m, x, nullptr, w, stride, 0.0, eg, egs, nullptr, R, slot, em, ef);
+    else
+      k_corners<F2, 1, true, false><<<cg, NT, 0, st>>>(m, x, nullptr, w, stride, 0.0, eg, egs, nullptr, R, slot, em, ef);
+    return;
+  }
+  const unsigned grid = elem_grid<FL>(m);
   if (stage == 0)
-    k_grad_elements<FL, 0, true><<<grid, block, 0, st>>>(m, x, w, stride, eg, egs, R, slot, em, ef);
+    k_grad_elements<FL, 0, true><<<grid, NT, 0, st>>>(m, x, w, stride, eg, egs, R, slot, em, ef);
   else if (use_ref)
-    k_grad_elements<FL, 1, true><<<grid, block, 0, st>>>(m, x, w, stride, eg, egs, R, slot, em, ef);
+    k_grad_elements<FL, 1, true><<<grid, NT, 0, st>>>(m, x, w, stride, eg, egs, R, slot, em, ef);
   else
-    k_grad_elements<FL, 1, false><<<grid, block, 0, st>>>(m, x, w, stride, eg, egs, R, slot, em, ef);
+    k_grad_elements<FL, 1, false><<<grid, NT, 0, st>>>(m, x, w, stride, eg, egs, R, slot, em, ef);
 }
 static void launch_grad_elements(cudaStream_t st, const MeshDev& m, int stage, int use_ref, const double* x,
                                  const double* w, long long stride, double* eg, long long egs, const Reduce& R, int slot,
@@ -513,8 +921,8 @@ static void launch_alpha0(cudaStream_t st, const double* s, const double* edge, 
 // lagged = x ; x += alpha*s on unfixed nodes ; dmax, dmax_relative   (update_coordinates.cpp:241-268, 94-118)
 __global__ void __launch_bounds__(NT) k_update(double* __restrict__ x, double* __restrict__ lag, const double* __restrict__ s,
                                                const double* __restrict__ edge, const uint8_t* __restrict__ fixed,
-                                               const double alpha, const long long n, const long long stride,
-                                               const Reduce R, const int slot) {
+                                               const uint8_t* __restrict__ owned, const double alpha, const long long n,
+                                               const long long stride, const Reduce R, const int slot) {
   double acc[2] = {0.0, 0.0};
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
     const bool fx = fixed[i] != 0;
@@ -530,7 +938,7 @@ __global__ void __launch_bounds__(NT) k_update(double* __restrict__ x, double* _
         maxDelta = a > maxDelta ? a : maxDelta;
       }
     }
-    if (!fx) {
+    if (!fx && (!owned || owned[i])) {  // deltas over owned nodes only (ghost copies have incomplete edge lengths)
       acc[0] = maxDelta > acc[0] ? maxDelta : acc[0];
       const double rel = maxDelta / edge[i];
       acc[1] = rel > acc[1] ? rel : acc[1];
@@ -539,8 +947,8 @@ __global__ void __launch_bounds__(NT) k_update(double* __restrict__ x, double* _
   grid_reduce<OpMax, 2, false>(acc, 0ull, R, slot);
 }
 static void launch_update(cudaStream_t st, double* x, double* lag, const double* s, const double* edge, const uint8_t* fixed,
-                          double alpha, long long n, long long stride, const Reduce& R, int slot) {
-  k_update<<<blas_blocks(n), NT, 0, st>>>(x, lag, s, edge, fixed, alpha, n, stride, R, slot);
+                          const uint8_t* owned, double alpha, long long n, long long stride, const Reduce& R, int slot) {
+  k_update<<<blas_blocks(n), NT, 0, st>>>(x, lag, s, edge, fixed, owned, alpha, n, stride, R, slot);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -663,26 +1071,24 @@ static void launch_unpack(cudaStream_t st, double* f, long long stride, int nc, 
 template <int FL>
 __global__ void __launch_bounds__(NT) k_elem_fixed_bits(const MeshDev m, const uint8_t* __restrict__ fixed,
                                                         uint8_t* __restrict__ bits) {
-  long long e, nid[8];
-  if (!element_of_thread<FL>(m, e, nid)) return;
-  unsigned b = 0;
-  constexpr int NN = npe<FL>();
+  const long long ntiles = num_tiles<FL>(m);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long e, nid[8];
+    if (!element_of_tile<FL>(m, tile, e, nid)) continue;
+    unsigned b = 0;
+    constexpr int NN = npe<FL>();
 #pragma unroll
-  for (int a = 0; a < NN; a++) b |= (fixed[nid[a]] ? 1u : 0u) << a;
-  bits[m.elem_off + e] = (uint8_t)b;
+    for (int a = 0; a < NN; a++) b |= (fixed[nid[a]] ? 1u : 0u) << a;
+    bits[m.elem_off + e] = (uint8_t)b;
+  }
 }
 static void launch_elem_fixed_bits(cudaStream_t st, const MeshDev& m, const uint8_t* fixed, uint8_t* bits) {
-  dim3 block, grid;
-  if (m.kind == KIND_SGRID) {
-    grid = elem_grid<FL_SGRID>(m, block);
-    k_elem_fixed_bits<FL_SGRID><<<grid, block, 0, st>>>(m, fixed, bits);
-  } else if (m.kind == KIND_HEX8) {
-    grid = elem_grid<FL_HEX8>(m, block);
-    k_elem_fixed_bits<FL_HEX8><<<grid, block, 0, st>>>(m, fixed, bits);
-  } else {
-    grid = elem_grid<FL_TET4>(m, block);
-    k_elem_fixed_bits<FL_TET4><<<grid, block, 0, st>>>(m, fixed, bits);
-  }
+  if (m.kind == KIND_SGRID)
+    k_elem_fixed_bits<FL_SGRID><<<elem_grid<FL_SGRID>(m), NT, 0, st>>>(m, fixed, bits);
+  else if (m.kind == KIND_HEX8)
+    k_elem_fixed_bits<FL_HEX8><<<elem_grid<FL_HEX8>(m), NT, 0, st>>>(m, fixed, bits);
+  else
+    k_elem_fixed_bits<FL_TET4><<<elem_grid<FL_TET4>(m), NT, 0, st>>>(m, fixed, bits);
 }
 
 static const Launchers g_launchers = {launch_metric,    launch_grad_elements, launch_grad_gather, launch_grad_fused_sgrid,
@@ -692,5 +1098,9 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_unpack,    launch_elem_fixed_bits};
 
 const Launchers* launchers() { return &g_launchers; }
+void set_variant(int metric_corners, int grad_corners) {
+  g_metric_corners = metric_corners;
+  g_grad_corners = grad_corners;
+}
 
 }  // namespace PMS_NS

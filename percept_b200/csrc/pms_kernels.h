@@ -40,7 +40,8 @@ struct Launchers {
   // metric of (x + alpha*s on unfixed nodes) vs reference w; result: out_d[slot] = sum, out_u[slot] = #invalid.
   // s may be null (alpha = 0).  elem_metric/elem_flag optional.
   void (*metric)(cudaStream_t, const MeshDev&, int stage, int use_ref, const double* x, const double* s, const double* w,
-                 long long stride, double alpha, const Reduce&, int slot, double* elem_metric, int32_t* elem_flag);
+                 long long stride, double alpha, const Reduce&, int slot, double* elem_metric, int32_t* elem_flag,
+                 const uint8_t* fixed);
   // element pass of the gradient: eg[(a*3+r)*eg_stride + e] (zero where the element is dropped); fused metric like above.
   void (*grad_elements)(cudaStream_t, const MeshDev&, int stage, int use_ref, const double* x, const double* w,
                         long long stride, double* eg, long long eg_stride, const Reduce&, int slot, double* elem_metric,
@@ -77,7 +78,7 @@ struct Launchers {
                  const Reduce&, int slot);
   // lagged = x ; x += alpha*s (unfixed) ; out_d[slot] = dmax, out_d[slot+1] = dmax_relative
   void (*update)(cudaStream_t, double* x, double* lagged, const double* s, const double* edge, const uint8_t* fixed,
-                 double alpha, long long n, long long stride, const Reduce&, int slot);
+                 const uint8_t* owned, double alpha, long long n, long long stride, const Reduce&, int slot);
   // edge lengths: el = sum over adjacent elements of mean edge length, na = adjacency count (division done by divide())
   void (*edge_lengths)(cudaStream_t, const MeshDev&, const double* w, long long stride, double* el, double* na);
   void (*divide)(cudaStream_t, double* el, const double* na, long long n);
@@ -90,5 +91,5 @@ struct Launchers {
 
 }  // namespace pmsk
 
-namespace pms_fast { const pmsk::Launchers* launchers(); }
-namespace pms_strict { const pmsk::Launchers* launchers(); }
+namespace pms_fast { const pmsk::Launchers* launchers(); void set_variant(int metric_corners, int grad_corners); }
+namespace pms_strict { const pmsk::Launchers* launchers(); void set_variant(int metric_corners, int grad_corners); }

@@ -98,7 +98,7 @@ def test_fused_metric_and_gradient_equals_separate_calls(kind):
     g1 = g.download("cg_g").copy()
     m2, n2 = g.total_metric(1, 0.0)
     g.get_gradient(1)
-    assert m1 == m2 and n1 == n2
+    assert n1 == n2 and abs(m1 - m2) <= 1e-14 * abs(m2)  # same math, different instruction schedule
     assert np.array_equal(g1, g.download("cg_g"))
     mo, no = o.metric_and_gradient(1)
     assert n1 == no and abs(m1 - mo) <= 1e-12 * abs(mo)

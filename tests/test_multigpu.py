@@ -1,0 +1,25 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box: `gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu`)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_partitioned_smoothing_matches_single_gpu(world):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29740 + world), os.path.join(ROOT, "tests", "mg_worker.py"), "6", "0.3"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
+    assert p.stdout.count("MGOK") == world

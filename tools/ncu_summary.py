@@ -28,3 +28,10 @@ for r in data:
     print(f"{name[:58]:58s} {us:8.1f} {g(r,'launch__registers_per_thread'):4.0f} {g(r,'sm__warps_active.avg.pct_of_peak_sustained_active'):6.1f} "
           f"{g(r,'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'):6.1f} {g(r,'smsp__issue_active.avg.pct_of_peak_sustained_active'):6.1f} "
           f"{g(r,'l1tex__throughput.avg.pct_of_peak_sustained_elapsed'):5.1f} {db/us/1e3:9.1f} {db/1e6:8.1f} {g(r,'smsp__inst_executed.sum')/1e6:8.2f}")
+    if "--stalls" in sys.argv:
+        st = {h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): g(r, h) for h in hdr
+              if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")}
+        top = sorted(st.items(), key=lambda kv: -kv[1])[:7]
+        print("      stalls/issue: " + "  ".join(f"{k}={v:.2f}" for k, v in top) +
+              f"   | eligible/cycle={g(r,'smsp__warps_eligible.avg.per_cycle_active'):.2f} active warps/smsp={g(r,'smsp__warps_active.avg.per_cycle_active'):.2f}"
+              f" local ld/st={g(r,'smsp__inst_executed_op_local_ld.sum',0)+g(r,'smsp__inst_executed_op_local_st.sum',0):.0f}")

@@ -23,8 +23,9 @@ def run(kind, nele, eps, reps=5):
     print(f"--- {kind} {nele}^3: {ne} elems, {nnod} nodes, setup {time.time()-t0:.1f}s")
     s = 1e-3 / nele * np.random.default_rng(0).standard_normal((3, nnod)); c.upload("cg_s", s)
     c.set_timing(1)
-    for stage in (0, 1):
-        for what in ("metric0", "metricA", "mgrad"):
+    ops = os.environ.get("QB_OPS", "metric0,metricA,mgrad").split(",")
+    for stage in [int(v) for v in os.environ.get("QB_STAGES", "0,1").split(",")]:
+        for what in ops:
             for it in range(reps + 2):
                 if it == 2: c.kernel_time_reset()
                 if what == "metric0": c.total_metric(stage, 0.0)
@@ -37,6 +38,7 @@ def run(kind, nele, eps, reps=5):
             extra = 0 if kind == "sgrid" else (32 if kind == "hex8" else 16) * ne
             gb = (bpn * nnod + extra) / 1e9
             print(f"stage {stage} {what:8s}: {ms:8.3f} ms  {ne/ms/1e6:8.2f} Gelem/s  alg {gb/ms*1e3:7.1f} GB/s ({gb/ms*1e3/6561.6*100:5.1f}% of 6561.6)")
+    if os.environ.get("QB_OPS"): c.close(); return
     # BLAS-1 style kernels
     for name, fn, bpn in (("dot", lambda: c.dot("cg_s", "cg_g"), 48), ("axpby", lambda: c.axpby(1.0, "cg_g", 0.5, "cg_s"), 72),
                           ("copy", lambda: c.copy_field("cg_d", "cg_s"), 48)):
