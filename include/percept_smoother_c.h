@@ -188,6 +188,13 @@ int pms_comm_init(pms_ctx* ctx, const void* id128, int rank, int nranks);
 int pms_set_halo(pms_ctx* ctx, int n_neighbors, const int* neighbor_ranks,
                  const int64_t* send_off, const int32_t* send_nodes,
                  const int64_t* recv_off, const int32_t* recv_nodes);
+/* Structured block per GPU: interface nodes are duplicated on every rank whose block contains them (as the
+ * reference duplicates them per block, gradient_functors.hpp:141-220).  For neighbour q, nodes[off[q]..off[q+1]) are
+ * my local copies of the nodes shared with q, in the same (global-id) order on both sides; neighbours in ascending
+ * rank order.  get_gradient / get_edge_lengths then sum the copies in ascending rank order (the multi-block ==
+ * single-block result).  owned (may be NULL): 1 where this rank is the lowest rank holding the node (dots, counts). */
+int pms_set_interface(pms_ctx* ctx, int n_neighbors, const int* neighbor_ranks, const int64_t* off,
+                      const int32_t* nodes, const uint8_t* owned);
 /* owner -> ghost copy of a nodal field (used for cg_s once per iteration).      */
 int pms_halo_exchange(pms_ctx* ctx, const char* name);
 

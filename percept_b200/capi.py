@@ -87,6 +87,7 @@ class Api:
         "comm_init": [C.c_void_p, C.c_int, C.c_int],
         "set_halo": [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         "halo_exchange": [C.c_char_p],
+        "set_interface": [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         "launch_count": [C.POINTER(C.c_uint64)],
         "stream": [C.POINTER(C.c_void_p)],
         "synchronize": [],
@@ -357,6 +358,14 @@ class Ctx:
         rn = np.ascontiguousarray(recv_nodes, dtype=np.int32)
         self._call("set_halo", int(nr.size), nr.ctypes.data, so.ctypes.data, sn.ctypes.data, ro.ctypes.data,
                    rn.ctypes.data)
+
+    def set_interface(self, neighbor_ranks, off, nodes, owned=None):
+        nr = np.ascontiguousarray(neighbor_ranks, dtype=np.int32)
+        of = np.ascontiguousarray(off, dtype=np.int64)
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        ow = None if owned is None else np.ascontiguousarray(owned, dtype=np.uint8)
+        self._call("set_interface", int(nr.size), nr.ctypes.data, of.ctypes.data, nd.ctypes.data,
+                   None if ow is None else ow.ctypes.data)
 
     def halo_exchange(self, name):
         self._call("halo_exchange", name.encode())

@@ -242,6 +242,7 @@ double op_dot(pms_ctx* c, const char* x, const char* y) {
 }
 
 void halo_exchange(pms_ctx* c, const char* name);
+void interface_sum(pms_ctx* c, DField& F);
 
 // total_metric(alpha), Def.hpp:330-388, without materialising x + alpha*s
 void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t* ninv, bool count_eval = true) {
@@ -294,7 +295,7 @@ void ensure_eg(pms_ctx* c) {
 }
 
 // get_gradient (Def.hpp:1481-1520); optionally the fused metric of the same pass
-void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv) {
+void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write_r = true) {
   DField& X = c->field("coordinates");
   DField& W = c->field("coordinates_NM1");
   DField& G = c->field("cg_g");
@@ -322,7 +323,7 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv) {
                           c->keep_elem ? c->d_elem_metric : nullptr, c->keep_elem ? c->d_elem_flag : nullptr);
       check_launch(c, "grad_elements");
       c->L->grad_gather(c->stream, c->dev_blocks[b], c->d_eg, c->Epad, c->d_fixed, c->structured ? nullptr : c->d_node_owned,
-                        G.d, c->structured ? nullptr : Rr.d, c->Npad);
+                        G.d, (c->structured || !write_r) ? nullptr : Rr.d, c->Npad);
       check_launch(c, "grad_gather");
     }
   }
@@ -331,8 +332,9 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv) {
     c->L->group_sum(c->stream, c->n_groups, c->d_grp_ptr, c->d_grp_nodes, G.d, 3, c->Npad);
     check_launch(c, "group_sum");
   }
+  if (c->structured) interface_sum(c, G);  // block-per-GPU: complete the sums over ranks
   G.version++;
-  if (!c->structured) Rr.version++;
+  if (!c->structured && write_r) Rr.version++;
   if (mtot) {
     fetch(c, 0, nb, nb);
     double m = 0.0;
@@ -369,6 +371,8 @@ void op_edge_lengths(pms_ctx* c) {
       c->L->group_sum(c->stream, c->n_groups, c->d_grp_ptr, c->d_grp_nodes, EL.d, 1, c->Npad);
       c->L->group_sum(c->stream, c->n_groups, c->d_grp_ptr, c->d_grp_nodes, NA.d, 1, c->Npad);
     }
+    interface_sum(c, EL);
+    interface_sum(c, NA);
     Timed t(c, FAM_EDGE);
     c->L->divide(c->stream, EL.d, NA.d, c->N);
     check_launch(c, "divide");
@@ -449,6 +453,28 @@ void halo_exchange(pms_ctx* c, const char* name) {
     c->L->unpack(c->stream, F.d, c->Npad, nc, c->d_recv_nodes + c->recv_off[q], cnt, c->d_recv_buf + 3 * c->recv_off[q]);
   }
   check_launch(c, "halo");
+  F.version++;
+}
+
+// sum a nodal field over the copies of interface nodes held by different ranks (structured block per GPU)
+void interface_sum(pms_ctx* c, DField& F) {
+  if (c->nranks <= 1 || c->if_ranks.empty()) return;
+  const int nc = F.ncomp, nn = (int)c->if_ranks.size();
+  Timed t(c, FAM_HALO, nn + 1);
+  for (int q = 0; q < nn; q++) {
+    const long long cnt = c->if_off[q + 1] - c->if_off[q];
+    c->L->pack(c->stream, F.d, c->Npad, nc, c->d_if_nodes + c->if_off[q], cnt, c->d_if_send + 3 * c->if_off[q]);
+  }
+  PMS_NCCL(g_nccl.GroupStart());
+  for (int q = 0; q < nn; q++) {
+    const long long cnt = c->if_off[q + 1] - c->if_off[q];
+    if (!cnt) continue;
+    PMS_NCCL(g_nccl.Send(c->d_if_send + 3 * c->if_off[q], cnt * nc, NCCL_F64, c->if_ranks[q], c->nccl_comm, c->stream));
+    PMS_NCCL(g_nccl.Recv(c->d_if_recv + 3 * c->if_off[q], cnt * nc, NCCL_F64, c->if_ranks[q], c->nccl_comm, c->stream));
+  }
+  PMS_NCCL(g_nccl.GroupEnd());
+  c->L->shared_sum(c->stream, c->n_shared, c->d_sh_nodes, c->d_sh_ptr, c->d_sh_pos, c->d_sh_cnt, c->d_if_recv, F.d, nc, c->Npad);
+  check_launch(c, "interface_sum");
   F.version++;
 }
 
@@ -569,7 +595,7 @@ struct Driver {
     {
       double m;
       uint64_t n;
-      op_gradient(c, st->stage, &m, &n);
+      op_gradient(c, st->stage, &m, &n, /*write_r=*/false);  // cg_r = cg_g (Def.hpp:1508) is overwritten by r = -g below
       st->n_gradient_evals++;
     }
     // r = -g ; dold = d.d ; dmid = r.d ; dnew = r.r   (Def.hpp:1034-1037)
@@ -733,7 +759,8 @@ void pms_destroy(pms_ctx* c) {
     void* ptrs[] = {c->d_conn,      c->d_fixed,     c->d_node_owned, c->d_elem_owned, c->d_dotmask,  c->d_elem_bits,
                     c->d_csr_ptr,   c->d_csr_ent,   c->d_grp_ptr,    c->d_grp_nodes,  c->d_eg,       c->d_elem_metric,
                     c->d_elem_flag, c->R.partial_d, c->R.partial_u,  c->R.ticket,     c->R.out_d,    c->R.out_u,
-                    c->d_send_nodes, c->d_recv_nodes, c->d_send_buf, c->d_recv_buf,   c->d_coll, c->d_skip};
+                    c->d_send_nodes, c->d_recv_nodes, c->d_send_buf, c->d_recv_buf,   c->d_coll, c->d_skip, c->d_csr_ent32, c->d_if_nodes, c->d_sh_nodes, c->d_sh_cnt, c->d_sh_ptr, c->d_sh_pos,
+                    c->d_if_send, c->d_if_recv};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->h_out_d) cudaFreeHost(c->h_out_d);
@@ -1060,6 +1087,10 @@ int pms_commit(pms_ctx* c) {
     }
     c->d_csr_ptr = dupload(c->h_csr_ptr);
     c->d_csr_ent = dupload(c->h_csr_ent);
+    if (c->E * 8 < (1ll << 31)) {
+      std::vector<int32_t> e32(c->h_csr_ent.begin(), c->h_csr_ent.end());
+      c->d_csr_ent32 = dupload(e32);
+    }
     if (!c->h_elem_owned.empty()) {
       std::vector<uint8_t> eo(c->Epad, 0);
       std::copy(c->h_elem_owned.begin(), c->h_elem_owned.end(), eo.begin());
@@ -1080,6 +1111,7 @@ int pms_commit(pms_ctx* c) {
     m.elem_owned = c->d_elem_owned;
     m.csr_ptr = c->d_csr_ptr;
     m.csr_ent = c->d_csr_ent;
+    m.csr_ent32 = c->d_csr_ent32;
     c->dev_blocks.push_back(m);
   }
 
@@ -1434,6 +1466,61 @@ int pms_set_halo(pms_ctx* c, int nn, const int* ranks, const int64_t* send_off, 
   c->d_recv_nodes = dupload(r);
   c->d_send_buf = dalloc<double>((size_t)3 * ns);
   c->d_recv_buf = dalloc<double>((size_t)3 * nr);
+  PMS_CATCH
+}
+
+int pms_set_interface(pms_ctx* c, int nn, const int* ranks, const int64_t* off, const int32_t* nodes, const uint8_t* owned) {
+  PMS_TRY
+  require_committed(c);
+  if (!c->structured) throw PmsError(PMS_ERR_ARG, "pms_set_interface is for structured blocks; unstructured meshes use pms_set_halo");
+  c->if_ranks.assign(ranks, ranks + nn);
+  c->if_off.assign(off, off + nn + 1);
+  const int64_t tot = c->if_off[nn];
+  for (int64_t i = 0; i < tot; i++)
+    if (nodes[i] < 0 || nodes[i] >= c->N) throw PmsError(PMS_ERR_ARG, "interface node out of range");
+  std::vector<int32_t> nd(nodes, nodes + tot);
+  c->d_if_nodes = dupload(nd);
+  c->d_if_send = dalloc<double>((size_t)3 * tot);
+  c->d_if_recv = dalloc<double>((size_t)3 * tot);
+  // per shared node: contributions in ascending rank order; neighbours are given in ascending rank order
+  std::map<int32_t, std::vector<std::pair<int, std::pair<int64_t, int32_t>>>> by_node;  // node -> (rank, (pos, cnt))
+  for (int q = 0; q < nn; q++) {
+    const int64_t cnt = c->if_off[q + 1] - c->if_off[q];
+    for (int64_t i = 0; i < cnt; i++)
+      by_node[nodes[c->if_off[q] + i]].push_back({ranks[q], {3 * c->if_off[q] + i, (int32_t)cnt}});
+  }
+  std::vector<int32_t> sh_nodes, sh_cnt;
+  std::vector<int64_t> sh_ptr{0}, sh_pos;
+  for (auto& kv : by_node) {
+    auto v = kv.second;
+    v.push_back({c->rank, {-1, 0}});
+    std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    sh_nodes.push_back(kv.first);
+    for (auto& e : v) {
+      sh_pos.push_back(e.second.first);
+      sh_cnt.push_back(e.second.second);
+    }
+    sh_ptr.push_back((int64_t)sh_pos.size());
+  }
+  c->n_shared = (long long)sh_nodes.size();
+  c->d_sh_nodes = dupload(sh_nodes);
+  c->d_sh_ptr = dupload(sh_ptr);
+  c->d_sh_pos = dupload(sh_pos);
+  c->d_sh_cnt = dupload(sh_cnt);
+  if (owned) {  // dot / node-count ownership: the lowest rank holding a copy counts the node
+    c->h_dotmask.assign(owned, owned + c->N);
+    c->dotmask_trivial = true;
+    c->num_nodes_owned = 0;
+    for (uint8_t v : c->h_dotmask) {
+      c->num_nodes_owned += v ? 1 : 0;
+      if (!v) c->dotmask_trivial = false;
+    }
+    if (!c->dotmask_trivial) {
+      if (!c->d_dotmask) c->d_dotmask = dalloc<uint8_t>(c->Npad);
+      PMS_CUDA(cudaMemset(c->d_dotmask, 0, c->Npad));
+      PMS_CUDA(cudaMemcpy(c->d_dotmask, c->h_dotmask.data(), c->N, cudaMemcpyHostToDevice));
+    }
+  }
   PMS_CATCH
 }
 

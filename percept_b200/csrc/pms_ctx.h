@@ -72,6 +72,7 @@ struct pms_ctx {
   uint8_t *d_fixed = nullptr, *d_node_owned = nullptr, *d_elem_owned = nullptr, *d_dotmask = nullptr, *d_elem_bits = nullptr,
           *d_skip = nullptr;
   int64_t *d_csr_ptr = nullptr, *d_csr_ent = nullptr;
+  int32_t* d_csr_ent32 = nullptr;
   int64_t *d_grp_ptr = nullptr, *d_grp_nodes = nullptr;
   long long n_groups = 0;
   double* d_eg = nullptr;  // element-gradient scratch [3*npe][Epad]
@@ -105,6 +106,13 @@ struct pms_ctx {
   int32_t *d_send_nodes = nullptr, *d_recv_nodes = nullptr;
   double *d_send_buf = nullptr, *d_recv_buf = nullptr;
   double* d_coll = nullptr;  // small device buffer for scalar allreduces
+  // cross-rank interface sums (structured block per GPU)
+  std::vector<int> if_ranks;
+  std::vector<int64_t> if_off;
+  int32_t *d_if_nodes = nullptr, *d_sh_nodes = nullptr, *d_sh_cnt = nullptr;
+  int64_t *d_sh_ptr = nullptr, *d_sh_pos = nullptr;
+  double *d_if_send = nullptr, *d_if_recv = nullptr;
+  long long n_shared = 0;
 
   // instrumentation
   uint64_t launches = 0;

@@ -50,20 +50,38 @@ PMS_DI void cross3(const double (&a)[3], const double (&b)[3], double (&c)[3]) {
 }
 PMS_DI double dot3(const double (&a)[3], const double (&b)[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
+// vertex accessors: V(p, r) = component r of the vertex at structured position p (node = i+2j+4k)
+struct RegVerts {  // vertices already in registers
+  const double (&v)[8][3];
+  PMS_DI explicit RegVerts(const double (&vv)[8][3]) : v(vv) {}
+  PMS_DI double operator()(int p, int r) const { return v[p][r]; }
+};
+template <bool EXODUS, int STRIDE>
+struct SmemVerts {  // vertices read in place from a thread-private shared-memory column sm[(a*3+r)*STRIDE]
+  const double* base;  // slot of (local node 0, comp 0) of the wanted array for this thread
+  PMS_DI explicit SmemVerts(const double* b) : base(b) {}
+  PMS_DI double operator()(int p, int r) const {
+    const int a = EXODUS ? (p == 2 ? 3 : (p == 3 ? 2 : (p == 6 ? 7 : (p == 7 ? 6 : p)))) : p;  // structured -> Exodus local node
+    return base[(a * 3 + r) * STRIDE];
+  }
+};
+
 // canonical edge along axis AX touching corner c (vertices in structured numbering node = i+2j+4k)
-template <int AX>
-PMS_DI void corner_edge(const double (&v)[8][3], int c, double (&e)[3]) {
+template <int AX, class V>
+PMS_DI void corner_edge(const V& v, int c, double (&e)[3]) {
   const int lo = c & ~(1 << AX), hi = lo | (1 << AX);
 #pragma unroll
-  for (int r = 0; r < 3; r++) e[r] = v[hi][r] - v[lo][r];
+  for (int r = 0; r < 3; r++) e[r] = v(hi, r) - v(lo, r);
 }
 
 // Hex element metric (+ gradient when GRAD) in structured vertex numbering.  STAGE 0 untangle, 1 ShapeB1 with
 // reference mesh.  grad[a][r] accumulates d(metric)/d(x_a,r); the caller applies the element-level validity rule.
-template <int STAGE, bool GRAD>
-PMS_DI double hex_metric_fast(const double (&vc)[8][3], const double (&vo)[8][3], bool& valid, double (&grad)[8][3]) {
+// Written branch-free (selects instead of `if (detA > 0)`): the 8 corners then sit in ONE basic block and ptxas can
+// interleave their dependent FP64 chains, which is what hides the ~9-cycle DFMA latency at 2 warps per scheduler.
+template <int STAGE, bool GRAD, class VC, class VO>
+PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double (&grad)[8][3]) {
   valid = true;
-  double val = 0.0;
+  double val0 = 0.0, val1 = 0.0;
   if (GRAD) {
 #pragma unroll
     for (int a = 0; a < 8; a++)
@@ -82,67 +100,61 @@ PMS_DI double hex_metric_fast(const double (&vc)[8][3], const double (&vo)[8][3]
     double K0[3], K1[3], K2[3];
     cross3(a1, a2, K0);
     const double detA = dot3(a0, K0);
-    if (detA <= 0.0) valid = false;
+    const bool ok = detA > 0.0;
+    if (!ok) valid = false;
     double dM[3][3];  // dM[r][s]: derivative w.r.t. component r of the edge along axis s
-    bool have = false;
     if (STAGE == 0) {
       double C0[3];
       cross3(w1, w2, C0);
       const double detW = dot3(w0, C0);
       const double vv = BETA_MULT * detW - detA;
-      if (vv > 0.0) {
-        val += vv * vv;
-        if (GRAD) {
-          have = true;
-          cross3(a2, a0, K1);
-          cross3(a0, a1, K2);
-          const double s = -2.0 * vv;
+      const double vp = vv > 0.0 ? vv : 0.0;  // contributes 0 (value and gradient) when vv <= 0
+      ((c & 1) ? val1 : val0) += vp * vp;
+      if (GRAD) {
+        cross3(a2, a0, K1);
+        cross3(a0, a1, K2);
+        const double s = -2.0 * vp;
 #pragma unroll
-          for (int r = 0; r < 3; r++) {
-            dM[r][0] = s * K0[r];
-            dM[r][1] = s * K1[r];
-            dM[r][2] = s * K2[r];
-          }
+        for (int r = 0; r < 3; r++) {
+          dM[r][0] = s * K0[r];
+          dM[r][1] = s * K1[r];
+          dM[r][2] = s * K2[r];
         }
       }
     } else {
-      if (detA > 0.0) {
-        double C0[3], C1[3], C2[3];
-        cross3(w1, w2, C0);
-        cross3(w2, w0, C1);
-        cross3(w0, w1, C2);
-        const double detW = dot3(w0, C0);
-        double Tp[3][3];
-        double y = 0.0;
+      double C0[3], C1[3], C2[3];
+      cross3(w1, w2, C0);
+      cross3(w2, w0, C1);
+      cross3(w0, w1, C2);
+      const double detW = dot3(w0, C0);
+      double Tp[3][3], ys[3];
 #pragma unroll
-        for (int r = 0; r < 3; r++)
+      for (int r = 0; r < 3; r++) {
 #pragma unroll
-          for (int s = 0; s < 3; s++) {
-            Tp[r][s] = a0[r] * C0[s] + a1[r] * C1[s] + a2[r] * C2[s];
-            y += Tp[r][s] * Tp[r][s];
-          }
-        const double P = FAC_3SQRT3 * fabs(detW) * detA;
-        const double rr = fast_rsqrt(y * P * P);
-        const double yr = y * rr;  // sqrt(y)/P
-        const double q = y * yr;   // y^1.5/P
-        val += q - detW;
-        if (GRAD) {
-          have = true;
-          cross3(a2, a0, K1);
-          cross3(a0, a1, K2);
-          const double k1 = 3.0 * yr;
-          const double nk2 = -q * fast_rcp(detA);
+        for (int s = 0; s < 3; s++) Tp[r][s] = a0[r] * C0[s] + a1[r] * C1[s] + a2[r] * C2[s];
+        ys[r] = Tp[r][0] * Tp[r][0] + Tp[r][1] * Tp[r][1] + Tp[r][2] * Tp[r][2];
+      }
+      const double y = (ys[0] + ys[1]) + ys[2];
+      const double P = FAC_3SQRT3 * fabs(detW) * detA;
+      const double rr = fast_rsqrt(ok ? y * P * P : 1.0);
+      const double yr = y * rr;  // sqrt(y)/P
+      const double q = y * yr;   // y^1.5/P
+      ((c & 1) ? val1 : val0) += ok ? q - detW : 0.0;
+      if (GRAD) {
+        cross3(a2, a0, K1);
+        cross3(a0, a1, K2);
+        const double k1 = ok ? 3.0 * yr : 0.0;
+        const double nk2 = ok ? -q * fast_rcp(detA) : 0.0;  // detA <= 0: corner contributes nothing (SmootherMetric.hpp:835)
 #pragma unroll
-          for (int r = 0; r < 3; r++) {
-            const double (&t)[3] = Tp[r];
-            dM[r][0] = k1 * (t[0] * C0[0] + t[1] * C0[1] + t[2] * C0[2]) + nk2 * K0[r];
-            dM[r][1] = k1 * (t[0] * C1[0] + t[1] * C1[1] + t[2] * C1[2]) + nk2 * K1[r];
-            dM[r][2] = k1 * (t[0] * C2[0] + t[1] * C2[1] + t[2] * C2[2]) + nk2 * K2[r];
-          }
+        for (int r = 0; r < 3; r++) {
+          const double (&t)[3] = Tp[r];
+          dM[r][0] = k1 * (t[0] * C0[0] + t[1] * C0[1] + t[2] * C0[2]) + nk2 * K0[r];
+          dM[r][1] = k1 * (t[0] * C1[0] + t[1] * C1[1] + t[2] * C1[2]) + nk2 * K1[r];
+          dM[r][2] = k1 * (t[0] * C2[0] + t[1] * C2[1] + t[2] * C2[2]) + nk2 * K2[r];
         }
       }
     }
-    if (GRAD && have) {
+    if (GRAD) {
 #pragma unroll
       for (int s = 0; s < 3; s++) {
         const int lo = c & ~(1 << s), hi = lo | (1 << s);
@@ -154,9 +166,74 @@ PMS_DI double hex_metric_fast(const double (&vc)[8][3], const double (&vo)[8][3]
       }
     }
   }
-  return val;
+  return val0 + val1;
 }
 
+template <int STAGE, bool GRAD>
+PMS_DI double hex_metric_fast(const double (&vc)[8][3], const double (&vo)[8][3], bool& valid, double (&grad)[8][3]) {
+  return hex_metric_fast_v<STAGE, GRAD>(RegVerts(vc), RegVerts(vo), valid, grad);
+}
+
+// ShapeB1 metric only, restructured for instruction-level parallelism: the per-corner dependent chains (9-term
+// Frobenius sum, rsqrt seed + 2 Newton steps) are the latency bottleneck at 2 warps per scheduler (ncu: "wait" is the
+// top stall), so phase 1 computes y_c, P_c, detW_c for all 8 corners (3-way split sums), phase 2 runs the 8
+// independent rsqrt/Newton chains interleaved.  Same arithmetic per corner as hex_metric_fast<1,false>.
+PMS_DI double hex_shapeb1_metric_ilp(const double (&vc)[8][3], const double (&vo)[8][3], bool& valid) {
+  double z[8], y[8], dW[8];
+  bool ok[8];
+  valid = true;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    double a0[3], a1[3], a2[3], w0[3], w1[3], w2[3];
+    corner_edge<0>(RegVerts(vc), c, a0);
+    corner_edge<1>(RegVerts(vc), c, a1);
+    corner_edge<2>(RegVerts(vc), c, a2);
+    corner_edge<0>(RegVerts(vo), c, w0);
+    corner_edge<1>(RegVerts(vo), c, w1);
+    corner_edge<2>(RegVerts(vo), c, w2);
+    double K0[3], C0[3], C1[3], C2[3];
+    cross3(a1, a2, K0);
+    const double detA = dot3(a0, K0);
+    ok[c] = detA > 0.0;
+    if (!ok[c]) valid = false;
+    cross3(w1, w2, C0);
+    cross3(w2, w0, C1);
+    cross3(w0, w1, C2);
+    dW[c] = dot3(w0, C0);
+    double ys[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const double t0 = a0[r] * C0[0] + a1[r] * C1[0] + a2[r] * C2[0];
+      const double t1 = a0[r] * C0[1] + a1[r] * C1[1] + a2[r] * C2[1];
+      const double t2 = a0[r] * C0[2] + a1[r] * C1[2] + a2[r] * C2[2];
+      ys[r] = t0 * t0 + t1 * t1 + t2 * t2;
+    }
+    y[c] = (ys[0] + ys[1]) + ys[2];
+    const double P = FAC_3SQRT3 * fabs(dW[c]) * detA;
+    z[c] = ok[c] ? y[c] * P * P : 1.0;
+  }
+  double r[8], hz[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r[c]) : "d"(z[c]));
+    hz[c] = 0.5 * z[c];
+  }
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    double e[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) e[c] = fma(-(hz[c] * r[c]), r[c], 0.5);
+#pragma unroll
+    for (int c = 0; c < 8; c++) r[c] = fma(r[c], e[c], r[c]);
+  }
+  double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    v0 += ok[c] ? y[c] * (y[c] * r[c]) - dW[c] : 0.0;
+    v1 += ok[c + 1] ? y[c + 1] * (y[c + 1] * r[c + 1]) - dW[c + 1] : 0.0;
+  }
+  return v0 + v1;
+}
 
 // One corner of a hex from its three edge vectors e_s = v[neighbour along s] - v[corner] (a* current, w* reference) and
 // the orientation sign p = (-1)^popc(c) that relates them to the canonical +axis frame.  Returns the corner's metric

@@ -371,10 +371,14 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
                                                    double* __restrict__ em, int32_t* __restrict__ ef) {
   constexpr bool FAST = fast_hex<FL, STAGE, USE_REF>();
   constexpr int NN = npe<FL>();
-  extern __shared__ double sm[];  // [NN*3*(WITH_S ? 3 : 2)][NTP]
+  // gradient of a hex on the fast path: vertices are read IN PLACE from shared memory (frees 96 registers for the
+  // 24 gradient accumulators + interleaved corner chains), so the prefetch targets the other of two buffers
+  constexpr bool INPLACE = FAST && GRAD && !WITH_S;
+  constexpr int NVAL = NN * 3 * (WITH_S ? 3 : 2);
+  extern __shared__ double sm[];  // [INPLACE ? 2 : 1][NVAL][NTP]
   const int tid = threadIdx.x;
-  double* my = sm + tid;
-  auto slot_of = [&](int arr, int a, int r) -> double* { return my + ((arr * NN + a) * 3 + r) * NTP; };
+  int buf = 0;
+  auto slot_in = [&](int b, int arr, int a, int r) -> double* { return sm + (size_t)b * NVAL * NTP + ((arr * NN + a) * 3 + r) * NTP + tid; };
 
   double val[1] = {0.0};
   unsigned long long inv = 0;
@@ -419,9 +423,9 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
           nid = conn_nn[a];
 #pragma unroll
         for (int r = 0; r < 3; r++) {
-          cp_async8(slot_of(0, a, r), &x[r * stride + nid]);
-          cp_async8(slot_of(1, a, r), &w[r * stride + nid]);
-          if (WITH_S) cp_async8(slot_of(2, a, r), &s[r * stride + nid]);
+          cp_async8(slot_in(buf, 0, a, r), &x[r * stride + nid]);
+          cp_async8(slot_in(buf, 1, a, r), &w[r * stride + nid]);
+          if (WITH_S) cp_async8(slot_in(buf, 2, a, r), &s[r * stride + nid]);
         }
       }
       if (WITH_S) bits_nxt = m.elem_fixed_bits[m.elem_off + e_nxt];
@@ -439,22 +443,25 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
     act_cur = act_nxt;
     bits_cur = bits_nxt;
     cp_async_wait_all();
+    const int cur = buf;  // buffer holding the current element
     double vc[8][3], vo[8][3];
-    if (act_cur) {
+    if (!INPLACE && act_cur) {
 #pragma unroll
       for (int a = 0; a < NN; a++)
 #pragma unroll
         for (int r = 0; r < 3; r++) {
-          double xv = *slot_of(0, a, r);
+          double xv = *slot_in(cur, 0, a, r);
           if (WITH_S) {
-            if (!((bits_cur >> a) & 1u)) xv += alpha * *slot_of(2, a, r);  // update_coordinates.cpp:255-256
+            if (!((bits_cur >> a) & 1u)) xv += alpha * *slot_in(cur, 2, a, r);  // update_coordinates.cpp:255-256
           }
           vc[vpos<FL, FAST>(a)][r] = xv;
-          vo[vpos<FL, FAST>(a)][r] = *slot_of(1, a, r);
+          vo[vpos<FL, FAST>(a)][r] = *slot_in(cur, 1, a, r);
         }
     }
-    // the values above are in registers before the slots are re-armed (same-thread program order on the LSU)
+    // single buffer: the values are in registers before the slots are re-armed (same-thread program order on the
+    // LSU); in-place mode: the next element goes to the other buffer
     asm volatile("" ::: "memory");
+    if (INPLACE) buf ^= 1;
     issue(tile + gridDim.x);
     if (FL != FL_SGRID) load_conn(tile + 2 * (long long)gridDim.x);
     if (!act_cur) continue;
@@ -462,7 +469,12 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
     bool valid;
     double mm;
     double grad[8][3];
-    if (FAST) {
+    if (INPLACE) {
+      const SmemVerts<FL == FL_HEX8, NTP> VC(slot_in(cur, 0, 0, 0)), VO(slot_in(cur, 1, 0, 0));
+      mm = hex_metric_fast_v<STAGE, GRAD>(VC, VO, valid, grad);
+    } else if (FAST && !GRAD && STAGE == 1) {
+      mm = hex_shapeb1_metric_ilp(vc, vo, valid);
+    } else if (FAST) {
       mm = hex_metric_fast<STAGE, GRAD>(vc, vo, valid, grad);
     } else if (GRAD) {
       mm = element_grad_metric<FL, STAGE, USE_REF>(vc, vo, valid, grad);
@@ -494,7 +506,8 @@ static void launch_elem_pipe(cudaStream_t st, const MeshDev& m, const double* x,
                              long long stride, double alpha, double* eg, long long egs, const Reduce& R, int slot,
                              double* em, int32_t* ef) {
   constexpr int NV = npe<FL>() * 3 * (WITH_S ? 3 : 2);
-  const size_t smem = (size_t)NV * NTP * sizeof(double);
+  constexpr bool INPLACE = fast_hex<FL, STAGE, USE_REF>() && GRAD && !WITH_S;
+  const size_t smem = (size_t)NV * NTP * sizeof(double) * (INPLACE ? 2 : 1);
   auto kern = k_elem_pipe<FL, STAGE, USE_REF, GRAD, WITH_S>;
   static int blocks_per_sm = 0;
   if (!blocks_per_sm) {
@@ -744,7 +757,7 @@ __global__ void __launch_bounds__(NT) k_grad_gather_csr(const MeshDev m, const d
   if (!skip) {
     const long long p0 = m.csr_ptr[n], p1 = m.csr_ptr[n + 1];
     for (long long p = p0; p < p1; p++) {
-      const long long ent = __ldg(&m.csr_ent[p]);
+      const long long ent = m.csr_ent32 ? (long long)__ldg(&m.csr_ent32[p]) : __ldg(&m.csr_ent[p]);
       const long long e = ent >> 3;
       const int a = (int)(ent & 7);
       g0 += __ldg(&eg[(long long)(a * 3 + 0) * egs + e]);
@@ -1068,6 +1081,34 @@ static void launch_unpack(cudaStream_t st, double* f, long long stride, int nc, 
   if (count > 0) k_unpack<<<blas_blocks(count), NT, 0, st>>>(f, stride, nc, nodes, count, buf);
 }
 
+// interface nodes duplicated on several ranks (structured block per GPU): f[node] = sum over all ranks holding a copy,
+// added in ascending rank order (entry pos < 0 = this rank's own value), so every copy ends bitwise identical
+__global__ void __launch_bounds__(NT) k_shared_sum(const long long nshared, const int32_t* __restrict__ nodes,
+                                                   const int64_t* __restrict__ ptr, const int64_t* __restrict__ ent_pos,
+                                                   const int32_t* __restrict__ ent_cnt, const double* __restrict__ recvbuf,
+                                                   double* __restrict__ f, const int ncomp, const long long stride) {
+  const long long j = (long long)blockIdx.x * NT + threadIdx.x;
+  if (j >= nshared) return;
+  const long long n = nodes[j];
+  for (int c = 0; c < ncomp; c++) {
+    double v = 0.0;
+    bool first = true;
+    for (long long p = ptr[j]; p < ptr[j + 1]; p++) {
+      const long long pos = ent_pos[p];
+      const double t = pos < 0 ? f[c * stride + n] : recvbuf[pos + (long long)c * ent_cnt[p]];
+      v = first ? t : v + t;
+      first = false;
+    }
+    // all copies read their own value before any write: own value is only read by this thread
+    f[c * stride + n] = v;
+  }
+}
+static void launch_shared_sum(cudaStream_t st, long long nshared, const int32_t* nodes, const int64_t* ptr, const int64_t* ent_pos,
+                              const int32_t* ent_cnt, const double* recvbuf, double* f, int ncomp, long long stride) {
+  if (nshared > 0)
+    k_shared_sum<<<(unsigned)((nshared + NT - 1) / NT), NT, 0, st>>>(nshared, nodes, ptr, ent_pos, ent_cnt, recvbuf, f, ncomp, stride);
+}
+
 template <int FL>
 __global__ void __launch_bounds__(NT) k_elem_fixed_bits(const MeshDev m, const uint8_t* __restrict__ fixed,
                                                         uint8_t* __restrict__ bits) {
@@ -1095,7 +1136,7 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_group_sum, launch_axpby,         launch_axpbypgz,    launch_set,
                                       launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,
-                                      launch_unpack,    launch_elem_fixed_bits};
+                                      launch_unpack,    launch_elem_fixed_bits, launch_shared_sum};
 
 const Launchers* launchers() { return &g_launchers; }
 void set_variant(int metric_corners, int grad_corners) {

@@ -25,6 +25,7 @@ struct MeshDev {
   const uint8_t* elem_owned;       // unstructured: 1 = locally owned element (metric sums these); may be null
   const int64_t* csr_ptr;          // unstructured node->element CSR
   const int64_t* csr_ent;          // entries elem*8+local, ascending
+  const int32_t* csr_ent32;        // same, 32-bit (when nelems*8 < 2^31): halves the gather's index traffic
 };
 
 struct Reduce {  // scratch for deterministic two-level reductions (partials + last-block ticket)
@@ -87,6 +88,9 @@ struct Launchers {
   void (*unpack)(cudaStream_t, double* f, long long stride, int ncomp, const int32_t* nodes, long long count, const double* buf);
   // per-element bit mask of fixed vertices
   void (*elem_fixed_bits)(cudaStream_t, const MeshDev&, const uint8_t* fixed, uint8_t* bits);
+  // cross-rank interface sum (structured block per GPU), ascending rank order
+  void (*shared_sum)(cudaStream_t, long long nshared, const int32_t* nodes, const int64_t* ptr, const int64_t* ent_pos,
+                     const int32_t* ent_cnt, const double* recvbuf, double* f, int ncomp, long long stride);
 };
 
 }  // namespace pmsk

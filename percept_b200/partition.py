@@ -231,6 +231,67 @@ def box_local_mesh(cells, procs, rank):
     return lm
 
 
+@dataclass
+class LocalBlock:
+    """One structured block per rank (BASELINE config 5): no ghost cells, interface nodes duplicated per block."""
+    node_size: tuple
+    origin: tuple                # global node index of local node (0,0,0)
+    node_gid: np.ndarray
+    fixed: np.ndarray            # global boundary nodes
+    owned: np.ndarray            # 1 where this rank is the lowest rank holding the node (dots / node count)
+    nb_ranks: np.ndarray
+    if_off: np.ndarray
+    if_nodes: np.ndarray
+    lattice: tuple
+
+    def global_lattice_coords(self, h):
+        NX, NY, NZ = self.lattice
+        g = self.node_gid
+        i = g % (NX + 1)
+        j = (g // (NX + 1)) % (NY + 1)
+        k = g // ((NX + 1) * (NY + 1))
+        return np.ascontiguousarray(np.stack([i * h, j * h, k * h]).astype(np.float64))
+
+
+def sgrid_block(cells, procs, rank):
+    """Block `rank` of the lattice cut into px*py*pz structured blocks, with the cross-rank interface lists
+    (shared nodes per neighbouring rank, ascending rank, each list in ascending global node id)."""
+    NX, NY, NZ = cells
+    px, py, pz = procs
+    b = _box_of_rank(rank, procs)
+    lo, hi = [], []
+    for d in range(3):
+        l, h_, _ = _ranges(cells[d], procs[d], b[d])
+        lo.append(l)
+        hi.append(h_)
+    nn = tuple(hi[d] - lo[d] + 1 for d in range(3))
+    ii, jj, kk = np.meshgrid(np.arange(nn[0]), np.arange(nn[1]), np.arange(nn[2]), indexing="ij")
+    ii, jj, kk = (a.transpose(2, 1, 0).reshape(-1) for a in (ii, jj, kk))
+    gi, gj, gk = ii + lo[0], jj + lo[1], kk + lo[2]
+    gid = gi + (NX + 1) * (gj + (NY + 1) * gk.astype(np.int64))
+    owner = (_owner_box_1d(gi, NX, px) + px * (_owner_box_1d(gj, NY, py) + py * _owner_box_1d(gk, NZ, pz))).astype(np.int32)
+    fixed = ((gi == 0) | (gi == NX) | (gj == 0) | (gj == NY) | (gk == 0) | (gk == NZ)).astype(np.uint8)
+    nb, off, nodes = [], [0], []
+    for r in range(px * py * pz):  # ascending rank
+        if r == rank:
+            continue
+        bb = _box_of_rank(r, procs)
+        if any(abs(bb[d] - b[d]) > 1 for d in range(3)):
+            continue
+        sel = np.ones(gid.size, dtype=bool)
+        for d, g in enumerate((gi, gj, gk)):
+            l, h_, _ = _ranges(cells[d], procs[d], bb[d])
+            sel &= (g >= l) & (g <= h_)
+        ids = np.nonzero(sel)[0]
+        if ids.size:
+            nb.append(r)
+            nodes.append(ids)  # ascending local id == ascending global id inside the shared face/edge/corner
+            off.append(off[-1] + ids.size)
+    return LocalBlock(node_size=nn, origin=tuple(lo), node_gid=gid, fixed=fixed, owned=(owner == rank).astype(np.uint8),
+                      nb_ranks=np.array(nb, np.int32), if_off=np.array(off, np.int64),
+                      if_nodes=np.concatenate(nodes).astype(np.int32) if nodes else np.zeros(0, np.int32), lattice=(NX, NY, NZ))
+
+
 def box_elem_rank(cells, procs):
     """Part id of every cell of the global lattice for the box decomposition (element id = ci + NX*(cj + NY*ck))."""
     NX, NY, NZ = cells

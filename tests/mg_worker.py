@@ -24,6 +24,9 @@ def main():
     h = 1.0 / n
     niter = int(sys.argv[1]) if len(sys.argv) > 1 else 6
     eps = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
+    mode = sys.argv[3] if len(sys.argv) > 3 else "hex8"
+    if mode == "sgrid":
+        return main_sgrid(rank, world, local, procs, n, cells, h, niter, eps)
 
     lm = part.box_local_mesh(cells, procs, rank)
     W = lm.global_lattice_coords(h)
@@ -85,6 +88,79 @@ def main():
         assert res["coord_rel"] < 1e-9 and res["final_metric_rel"] < 1e-9, res
         assert st.num_nodes == ss.num_nodes == ngl
     assert ghost_ok, f"rank {rank}: ghost coordinates differ from owner coordinates"
+    dist.barrier()
+    dist.destroy_process_group()
+    print("MGOK", rank, flush=True)
+
+
+def nccl_uid(rank):
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        assert pb.lib.pms_comm_unique_id(buf) == 0
+        uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    uid = uid.cuda()
+    dist.broadcast(uid, 0)
+    return uid.cpu().numpy().tobytes()
+
+
+def main_sgrid(rank, world, local, procs, n, cells, h, niter, eps):
+    """One structured block per GPU (BASELINE config 5) vs the single block holding the whole lattice."""
+    lb = part.sgrid_block(cells, procs, rank)
+    W = lb.global_lattice_coords(h)
+    X = part.perturb_by_global_id(W, lb.node_gid, lb.fixed, eps * h, seed=3)
+    c = pb.create(local)
+    c.add_structured_block(lb.node_size)
+    c.set_fixed_mask(lb.fixed)
+    c.commit()
+    c.comm_init(nccl_uid(rank), rank, world)
+    c.set_interface(lb.nb_ranks, lb.if_off, lb.if_nodes, lb.owned)
+    for f, v in (("coordinates", X), ("coordinates_N", X), ("coordinates_NM1", W)):
+        c.upload(f, v)
+    m1, n1 = c.metric_and_gradient(1)
+    g_local = c.download("cg_g")
+    c.get_edge_lengths()
+    el_local = c.download("cg_edge_length")
+    st = c.run_algorithm(niter, 0.0)
+    x_local = c.download("coordinates")
+    ngl = (cells[0] + 1) * (cells[1] + 1) * (cells[2] + 1)
+
+    def assemble(f):
+        full = torch.zeros((f.shape[0], ngl), dtype=torch.float64, device="cuda")
+        o = lb.owned == 1
+        full[:, torch.from_numpy(lb.node_gid[o]).cuda()] = torch.from_numpy(np.ascontiguousarray(f[:, o])).cuda()
+        dist.all_reduce(full)
+        return full.cpu().numpy()
+    xg, gg, eg = assemble(x_local), assemble(g_local), assemble(el_local)
+    copies_ok = np.array_equal(xg[:, lb.node_gid], x_local) and np.array_equal(gg[:, lb.node_gid], g_local)
+    if rank == 0:
+        NXn, NYn, NZn = cells[0] + 1, cells[1] + 1, cells[2] + 1
+        gid = np.arange(ngl)
+        one = part.sgrid_block(cells, (1, 1, 1), 0)
+        W1 = one.global_lattice_coords(h)
+        X1 = part.perturb_by_global_id(W1, one.node_gid, one.fixed, eps * h, seed=3)
+        s = pb.create(local)
+        s.add_structured_block((NXn, NYn, NZn))
+        s.set_fixed_mask(one.fixed)
+        s.commit()
+        for f, v in (("coordinates", X1), ("coordinates_N", X1), ("coordinates_NM1", W1)):
+            s.upload(f, v)
+        ms, ns = s.metric_and_gradient(1)
+        gs = s.download("cg_g")
+        s.get_edge_lengths()
+        es = s.download("cg_edge_length")
+        ss = s.run_algorithm(niter, 0.0)
+        xs = s.download("coordinates")
+        rel = lambda a, b: np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+        res = {"metric_rel": abs(m1 - ms) / abs(ms), "ninv": (n1, ns), "grad_rel": rel(gg, gs), "edge_rel": rel(eg, es),
+               "coord_rel": rel(xg, xs), "final_metric_rel": abs(st.global_metric - ss.global_metric) / abs(ss.global_metric),
+               "copies_ok": bool(copies_ok), "num_nodes": (int(st.num_nodes), int(ss.num_nodes))}
+        print("MGRESULT", res, flush=True)
+        # SGridSmootherMultiBlockvsSingleBlock.cpp tolerances: mtot 1e-10, nodal cg_g 1e-12, edge_len 1e-12
+        assert n1 == ns and res["metric_rel"] < 1e-12 and res["grad_rel"] < 1e-12 and res["edge_rel"] < 1e-12, res
+        assert res["coord_rel"] < 1e-9 and res["final_metric_rel"] < 1e-9, res
+        assert st.num_nodes == ss.num_nodes == ngl
+    assert copies_ok, f"rank {rank}: interface copies differ"
     dist.barrier()
     dist.destroy_process_group()
     print("MGOK", rank, flush=True)
