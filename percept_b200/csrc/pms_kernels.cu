@@ -34,7 +34,8 @@ constexpr bool STRICT = false;  // flop-reduced hex formulation (pms_device_fast
 template <int FL, int STAGE, bool USE_REF>
 __host__ __device__ constexpr bool fast_hex() { return !STRICT && FL != FL_TET4 && (STAGE == 0 || USE_REF); }
 
-constexpr int NT = 256;  // threads per block for all kernels
+constexpr int NT = 256;   // threads per block of the simple kernels
+constexpr int NTP = 128;  // threads per block of the pipelined / quad-lane element kernels
 constexpr int TBX = 32, TBY = 4, TBZ = 2;  // structured cell tile per block
 
 // ------------------------------------------------------------------------------------------------
@@ -314,6 +315,193 @@ static dim3 corner_grid(const MeshDev& m) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Quad-lane hex kernels (default build): 4 lanes per hex; lane q = (di,dj) owns the vertical edge of the hex at that
+// (i,j) corner, i.e. the two nodes (di,dj,0) and (di,dj,1), and evaluates the two corner Jacobians at those nodes.
+// The i- and j-neighbours' vertices come from lanes q^1 and q^2 by warp shuffle, the k-neighbour is the lane's own
+// other node.  Compared with one hex per thread this needs ~130 instead of ~250 registers (3-4 CTAs per SM instead
+// of 2) and still gives two independent corner chains per thread; compared with 8 lanes per hex it halves the
+// shuffle traffic per FP64 instruction.  Structured blocks march in k: the top nodes of one step are the bottom
+// nodes of the next, so each step loads one node per lane and shuffles one level.
+// ------------------------------------------------------------------------------------------------
+constexpr int QT_I = 8, QT_J = 4;  // structured tile per CTA and k-layer: 8 x 4 hexes (one j-row per warp)
+constexpr int QT_KCHUNK = 64;
+
+struct QNode {  // one node's current (x) and reference (w) position
+  double x[3], w[3];
+};
+
+template <bool WITH_S>
+__device__ __forceinline__ void qload(QNode& n, const bool active, const long long node, const double* __restrict__ x,
+                                      const double* __restrict__ s, const double* __restrict__ w, const long long stride,
+                                      const double alpha, const uint8_t* __restrict__ fixed) {
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    n.x[r] = 0.0;
+    n.w[r] = 0.0;
+  }
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      double xv = __ldg(&x[r * stride + node]);
+      if (WITH_S) {
+        if (!fixed[node]) xv += alpha * __ldg(&s[r * stride + node]);  // update_coordinates.cpp:255-256
+      }
+      n.x[r] = xv;
+      n.w[r] = __ldg(&w[r * stride + node]);
+    }
+  }
+}
+__device__ __forceinline__ void qshfl(const QNode& me, QNode& out, const int lanemask) {
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    out.x[r] = __shfl_xor_sync(0xffffffffu, me.x[r], lanemask);
+    out.w[r] = __shfl_xor_sync(0xffffffffu, me.w[r], lanemask);
+  }
+}
+
+// the two corners of this lane's vertical edge; n0/n1 own nodes, i0/j0/i1/j1 the shuffled neighbours per level
+template <int FL, int STAGE, bool GRAD>
+__device__ __forceinline__ void quad_body(const MeshDev& m, const bool active, const long long e, const int lane, const int q,
+                                          const QNode& n0, const QNode& n1, const QNode& i0, const QNode& j0, const QNode& i1,
+                                          const QNode& j1, double* __restrict__ eg, const long long eg_stride,
+                                          double* __restrict__ em, int32_t* __restrict__ ef, double& val,
+                                          unsigned long long& inv) {
+  double a[3][3], ww[3][3], dM0[3][3], dM1[3][3], detA0, detA1;
+  bool have0, have1;
+  const double p0 = (__popc(q) & 1) ? -1.0 : 1.0;
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    a[0][r] = i0.x[r] - n0.x[r];
+    a[1][r] = j0.x[r] - n0.x[r];
+    a[2][r] = n1.x[r] - n0.x[r];
+    ww[0][r] = i0.w[r] - n0.w[r];
+    ww[1][r] = j0.w[r] - n0.w[r];
+    ww[2][r] = n1.w[r] - n0.w[r];
+  }
+  const double mm0 = hex_corner_fast<STAGE, GRAD>(a[0], a[1], a[2], ww[0], ww[1], ww[2], p0, detA0, dM0, have0);
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    a[0][r] = i1.x[r] - n1.x[r];
+    a[1][r] = j1.x[r] - n1.x[r];
+    a[2][r] = n0.x[r] - n1.x[r];
+    ww[0][r] = i1.w[r] - n1.w[r];
+    ww[1][r] = j1.w[r] - n1.w[r];
+    ww[2][r] = n0.w[r] - n1.w[r];
+  }
+  const double mm1 = hex_corner_fast<STAGE, GRAD>(a[0], a[1], a[2], ww[0], ww[1], ww[2], -p0, detA1, dM1, have1);
+  const unsigned bal = __ballot_sync(0xffffffffu, detA0 > 0.0 && detA1 > 0.0);
+  const bool valid = ((bal >> (lane & 28)) & 0xfu) == 0xfu;  // all 8 corners of this hex
+  bool counted = active;
+  if (FL != FL_SGRID && m.elem_owned && active) counted = m.elem_owned[e] != 0;
+  if (counted) {
+    val += mm0 + mm1;
+    if (q == 0) inv += valid ? 0 : 1;
+  }
+  if (em) {
+    double t = mm0 + mm1;
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    if (active && q == 0) {
+      em[m.elem_off + e] = counted ? t : 0.0;
+      if (ef) ef[m.elem_off + e] = counted ? (valid ? 0 : 1) : 0;
+    }
+  }
+  if (GRAD) {
+    const bool u0 = have0 && (valid || STAGE == 0), u1 = have1 && (valid || STAGE == 0);  // gradient_functors.hpp:391
+    double g0[3], g1[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const double m00 = u0 ? dM0[r][0] : 0.0, m01 = u0 ? dM0[r][1] : 0.0, m02 = u0 ? dM0[r][2] : 0.0;
+      const double m10 = u1 ? dM1[r][0] : 0.0, m11 = u1 ? dM1[r][1] : 0.0, m12 = u1 ? dM1[r][2] : 0.0;
+      const double ri0 = __shfl_xor_sync(0xffffffffu, m00, 1), rj0 = __shfl_xor_sync(0xffffffffu, m01, 2);
+      const double ri1 = __shfl_xor_sync(0xffffffffu, m10, 1), rj1 = __shfl_xor_sync(0xffffffffu, m11, 2);
+      g0[r] = ((ri0 + rj0) + m12) - ((m00 + m01) + m02);
+      g1[r] = ((ri1 + rj1) + m02) - ((m10 + m11) + m12);
+    }
+    if (active) {
+      const int a0 = (FL == FL_HEX8) ? (q ^ ((q >> 1) & 1)) : q;  // structured corner -> Exodus local node
+      const long long ge = m.elem_off + e;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        eg[(long long)(a0 * 3 + r) * eg_stride + ge] = g0[r];
+        eg[(long long)((a0 + 4) * 3 + r) * eg_stride + ge] = g1[r];
+      }
+    }
+  }
+}
+
+#ifndef QUAD_MINB
+#define QUAD_MINB 3
+#endif
+template <int FL, int STAGE, bool GRAD, bool WITH_S>
+__global__ void __launch_bounds__(NTP, QUAD_MINB) k_quads(const MeshDev m, const double* __restrict__ x,
+                                                          const double* __restrict__ s, const double* __restrict__ w,
+                                                          const long long stride, const double alpha, double* __restrict__ eg,
+                                                          const long long eg_stride, const uint8_t* __restrict__ fixed,
+                                                          const Reduce R, const int slot, double* __restrict__ em,
+                                                          int32_t* __restrict__ ef) {
+  const int lane = threadIdx.x & 31, q = lane & 3, warp = threadIdx.x >> 5, hx = lane >> 2;
+  double val[1] = {0.0};
+  unsigned long long inv = 0;
+  if (FL == FL_SGRID) {
+    const int nci = m.ni - 1, ncj = m.nj - 1, nck = m.nk - 1;
+    const int nbx = (nci + QT_I - 1) / QT_I;
+    const int bx = blockIdx.x % nbx, by = blockIdx.x / nbx;
+    const int i = bx * QT_I + hx, j = by * QT_J + warp;
+    const bool active = i < nci && j < ncj;
+    const int k0 = blockIdx.y * QT_KCHUNK, k1 = min(k0 + QT_KCHUNK, nck);
+    const long long sk = (long long)m.ni * m.nj, se = (long long)nci * ncj;
+    long long node = m.node_off + (i + (q & 1)) + (long long)m.ni * (j + (q >> 1)) + sk * k0;
+    long long e = i + (long long)nci * j + se * k0;
+    QNode n0, n1, i0, j0, i1, j1;
+    qload<WITH_S>(n0, active, node, x, s, w, stride, alpha, fixed);
+    qshfl(n0, i0, 1);
+    qshfl(n0, j0, 2);
+    for (int k = k0; k < k1; k++, e += se) {
+      node += sk;
+      qload<WITH_S>(n1, active, node, x, s, w, stride, alpha, fixed);
+      qshfl(n1, i1, 1);
+      qshfl(n1, j1, 2);
+      quad_body<FL, STAGE, GRAD>(m, active, e, lane, q, n0, n1, i0, j0, i1, j1, eg, eg_stride, em, ef, val[0], inv);
+      n0 = n1;
+      i0 = i1;
+      j0 = j1;
+    }
+  } else {
+    const long long ntiles = (m.nelems + 31) / 32;
+    const int a0 = q ^ ((q >> 1) & 1);  // Exodus local node of structured corner q
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long e = tile * 32 + warp * 8 + hx;
+      const bool active = e < m.nelems;
+      long long nd0 = 0, nd1 = 0;
+      if (active) {
+        nd0 = __ldg(&m.conn[(long long)a0 * m.conn_stride + e]);
+        nd1 = __ldg(&m.conn[(long long)(a0 + 4) * m.conn_stride + e]);
+      }
+      QNode n0, n1, i0, j0, i1, j1;
+      qload<WITH_S>(n0, active, nd0, x, s, w, stride, alpha, fixed);
+      qload<WITH_S>(n1, active, nd1, x, s, w, stride, alpha, fixed);
+      qshfl(n0, i0, 1);
+      qshfl(n0, j0, 2);
+      qshfl(n1, i1, 1);
+      qshfl(n1, j1, 2);
+      quad_body<FL, STAGE, GRAD>(m, active, e, lane, q, n0, n1, i0, j0, i1, j1, eg, eg_stride, em, ef, val[0], inv);
+    }
+  }
+  grid_reduce<OpSum, 1, true>(val, inv, R, slot);
+}
+
+template <int FL>
+static dim3 quad_grid(const MeshDev& m) {
+  if (FL == FL_SGRID)
+    return dim3((unsigned)(((m.ni - 1 + QT_I - 1) / QT_I) * ((m.nj - 1 + QT_J - 1) / QT_J)),
+                (unsigned)((m.nk - 1 + QT_KCHUNK - 1) / QT_KCHUNK), 1);
+  const long long nt = (m.nelems + 31) / 32;
+  const long long cap = 148LL * 16;
+  return dim3((unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), 1, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Software-pipelined element kernel (default build, all element kinds): one element per thread, persistent CTAs of
 // NTP threads.  While a thread evaluates element t, the vertex data of its next element (x, [s], w for 8 or 4 nodes)
 // is already in flight: cp.async (LDGSTS) gathers it into a THREAD-PRIVATE column of shared memory
@@ -321,7 +509,6 @@ static dim3 corner_grid(const MeshDev& m) {
 // Memory latency is thus hidden behind ~2k instructions of FP64 work instead of by occupancy, which the ~170-250
 // registers per thread of the hex metric do not allow.
 // ------------------------------------------------------------------------------------------------
-constexpr int NTP = 128;
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -586,6 +773,15 @@ static void launch_metric2(cudaStream_t st, const MeshDev& m, const double* x, c
       launch_elem_pipe<FL, STAGE, USE_REF, false, false>(st, m, x, s, w, stride, alpha, nullptr, 0, R, slot, em, ef);
     return;
   }
+  if (fast_hex<FL, STAGE, USE_REF>() && g_metric_corners == 3 && FL != FL_TET4) {
+    constexpr int F2 = FL == FL_TET4 ? FL_HEX8 : FL;
+    const dim3 qg = quad_grid<F2>(m);
+    if (s && alpha != 0.0)
+      k_quads<F2, STAGE, false, true><<<qg, NTP, 0, st>>>(m, x, s, w, stride, alpha, nullptr, 0, fixed, R, slot, em, ef);
+    else
+      k_quads<F2, STAGE, false, false><<<qg, NTP, 0, st>>>(m, x, s, w, stride, alpha, nullptr, 0, fixed, R, slot, em, ef);
+    return;
+  }
   if (fast_hex<FL, STAGE, USE_REF>() && g_metric_corners == 1 && FL != FL_TET4) {
     constexpr int F2 = FL == FL_TET4 ? FL_HEX8 : FL;
     const dim3 cg = corner_grid<F2>(m);
@@ -684,6 +880,15 @@ static void launch_grad_elements1(cudaStream_t st, const MeshDev& m, int stage, 
       launch_elem_pipe<FL, 1, true, true, false>(st, m, x, nullptr, w, stride, 0.0, eg, egs, R, slot, em, ef);
     else
       launch_elem_pipe<FL, 1, false, true, false>(st, m, x, nullptr, w, stride, 0.0, eg, egs, R, slot, em, ef);
+    return;
+  }
+  if (!STRICT && FL != FL_TET4 && g_grad_corners == 3 && (stage == 0 || use_ref)) {
+    constexpr int F2 = FL == FL_TET4 ? FL_HEX8 : FL;
+    const dim3 qg = quad_grid<F2>(m);
+    if (stage == 0)
+      k_quads<F2, 0, true, false><<<qg, NTP, 0, st>>>(m, x, nullptr, w, stride, 0.0, eg, egs, nullptr, R, slot, em, ef);
+    else
+      k_quads<F2, 1, true, false><<<qg, NTP, 0, st>>>(m, x, nullptr, w, stride, 0.0, eg, egs, nullptr, R, slot, em, ef);
     return;
   }
   if (!STRICT && FL != FL_TET4 && g_grad_corners == 1 && (stage == 0 || use_ref)) {

@@ -274,3 +274,79 @@ def test_errors_are_reported_not_swallowed():
         g.dot("cg_g", "no_such_field")
     with pytest.raises(pb.SmootherError):
         g.total_metric(2, 0.0)
+
+
+@pytest.mark.parametrize("kind", ["sgrid", "hex8"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_kernel_variants_agree_with_oracle(kind, variant):
+    """All default-build hex kernel variants (0 simple, 1 corner-parallel, 2 pipelined, 3 quad-lane) against the oracle."""
+    for stage, eps in ((1, 0.25), (0, 1.0), (1, 1.0)):
+        g, o = pair(kind, 11, eps, strict=0)
+        g.set_option("variant_metric_corners", variant)
+        g.set_option("variant_grad_corners", variant)
+        n = g.num_nodes_local
+        s = meshes.seeded_field(n, 5, 0.01 / 11)
+        g.upload("cg_s", s)
+        o.upload("cg_s", s)
+        for alpha in (0.0, 0.7):
+            mg, ng = g.total_metric(stage, alpha)
+            mo, no = o.total_metric(stage, alpha)
+            assert ng == no and abs(mg - mo) <= 1e-12 * abs(mo)
+            assert rel(g.element_metrics()[0], o.element_metrics()[0]) < 1e-12
+        mg, ng = g.metric_and_gradient(stage)
+        mo, no = o.metric_and_gradient(stage)
+        assert ng == no and abs(mg - mo) <= 1e-12 * abs(mo)
+        assert rel(g.download("cg_g"), o.download("cg_g")) < 1e-12
+    g.set_option("variant_metric_corners", 2)
+    g.set_option("variant_grad_corners", 2)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("variant", [0, 2, 3])
+def test_anisotropic_odd_sized_mesh(kind, variant):
+    """Non-cubic node counts that are not multiples of any tile size (13 x 7 x 5 cells)."""
+    from tests.orc import fixture_cube
+    nn = (14, 8, 6)
+    W = fixture_cube(nn)
+    i = np.arange(nn[0])[None, None, :]
+    j = np.arange(nn[1])[None, :, None]
+    k = np.arange(nn[2])[:, None, None]
+    bm = ((i == 0) | (i == nn[0] - 1) | (j == 0) | (j == nn[1] - 1) | (k == 0) | (k == nn[2] - 1))
+    bm = np.ascontiguousarray(np.broadcast_to(bm, (nn[2], nn[1], nn[0])).reshape(-1).astype(np.uint8))
+    rng = np.random.default_rng(2)
+    X = np.ascontiguousarray(W + 0.25 / 13 * (rng.random(W.shape) - 0.5) * (bm == 0)[None, :])
+    ci, cj, ck = np.meshgrid(np.arange(nn[0] - 1), np.arange(nn[1] - 1), np.arange(nn[2] - 1), indexing="ij")
+    ci, cj, ck = (a.transpose(2, 1, 0).reshape(-1) for a in (ci, cj, ck))
+    nid = lambda a, b, c: a + nn[0] * (b + nn[1] * c)
+    offs = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    hexc = np.ascontiguousarray(np.stack([nid(ci + a, cj + b, ck + c) for a, b, c in offs], axis=1).astype(np.int32))
+    paths = [(1, 2), (2, 3), (3, 7), (7, 4), (4, 5), (5, 1)]
+    tetc = np.ascontiguousarray(np.stack([hexc[:, [0, a, b, 6]] for a, b in paths], axis=1).reshape(-1, 4).astype(np.int32))
+
+    def mk(api, opts):
+        c = api.create()
+        for kk, v in opts.items():
+            c.set_option(kk, v)
+        if kind == "sgrid":
+            b = c.add_structured_block(nn)
+            c.add_fixture_1_bcs(b)
+            c.select_boundary_sgrid()
+        else:
+            c.set_unstructured(8 if kind == "hex8" else 4, W.shape[1], hexc if kind == "hex8" else tetc)
+            c.set_fixed_mask(bm)
+        c.commit()
+        for f, v in (("coordinates", X), ("coordinates_N", X), ("coordinates_NM1", W)):
+            c.upload(f, v)
+        return c
+    g = mk(pb.api, {"variant_metric_corners": variant, "variant_grad_corners": variant, "cache_metric": 0})
+    o = mk(oracle, {"real_is_double": 1})
+    for stage in (0, 1):
+        mg, ng = g.metric_and_gradient(stage)
+        mo, no = o.metric_and_gradient(stage)
+        assert ng == no and abs(mg - mo) <= 1e-12 * max(abs(mo), 1e-300)
+        if np.max(np.abs(o.download("cg_g"))) > 0:
+            assert rel(g.download("cg_g"), o.download("cg_g")) < 1e-12
+    sg, so = g.run_algorithm(5, 0.0), o.run_algorithm(5, 0.0)
+    assert rel(g.download("coordinates"), o.download("coordinates")) < 1e-9
+    g.set_option("variant_metric_corners", 2)
+    g.set_option("variant_grad_corners", 2)

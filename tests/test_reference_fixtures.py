@@ -173,3 +173,60 @@ def test_gpu_smoothing_of_reference_fixture_meshes(name, topo, h):
         assert sg.num_invalid == so.num_invalid
         d = np.max(np.abs(g.download("coordinates") - o.download("coordinates")))
         assert d <= 1e-9
+
+
+def test_skin_selection_finds_the_cube_faces():
+    from percept_b200 import exodus
+    for name, topo, h in CASES:
+        W, conn, fixed = load(name)
+        assert np.array_equal(exodus.skin_nodes(conn, topo), fixed)  # skin of the unit cube == its six faces
+
+
+def test_exodus_reader_roundtrip(tmp_path):
+    """Write a tiny classic-netCDF Exodus file the way the reference fixtures are laid out and read it back."""
+    from scipy.io import netcdf_file
+    from percept_b200 import exodus
+    W, conn, _ = load("hex8_ref.npz")
+    p = str(tmp_path / "m.e")
+    nc = netcdf_file(p, "w", version=1)
+    nc.createDimension("num_nodes", W.shape[1])
+    nc.createDimension("num_el_in_blk1", conn.shape[0])
+    nc.createDimension("num_nod_per_el1", 8)
+    for i, n in enumerate(("coordx", "coordy", "coordz")):
+        v = nc.createVariable(n, "d", ("num_nodes",))
+        v[:] = W[i]
+    c = nc.createVariable("connect1", "i", ("num_el_in_blk1", "num_nod_per_el1"))
+    c[:] = conn + 1
+    c.elem_type = b"HEX8"
+    nc.close()
+    m = exodus.read_exodus(p)
+    assert np.array_equal(m["coords"], W) and m["blocks"][0][0] == 8 and np.array_equal(m["blocks"][0][1], conn)
+
+
+@pytest.mark.gpu
+def test_smooth_cli_on_reference_fixture(tmp_path):
+    """mesh_adapt-style entry point on hex8-ref (written as Exodus, perturbed), skin fixed."""
+    from scipy.io import netcdf_file
+    from percept_b200 import smooth
+    W, conn, fixed = load("hex8_ref.npz")
+    X = perturbed(W, fixed, 0.4 / 12)
+
+    def write(path, C):
+        nc = netcdf_file(path, "w", version=1)
+        nc.createDimension("num_nodes", C.shape[1])
+        nc.createDimension("num_el_in_blk1", conn.shape[0])
+        nc.createDimension("num_nod_per_el1", 8)
+        for i, n in enumerate(("coordx", "coordy", "coordz")):
+            v = nc.createVariable(n, "d", ("num_nodes",))
+            v[:] = C[i]
+        c = nc.createVariable("connect1", "i", ("num_el_in_blk1", "num_nod_per_el1"))
+        c[:] = conn + 1
+        nc.close()
+    write(str(tmp_path / "x.e"), X)
+    write(str(tmp_path / "w.e"), W)
+    smooth.main([str(tmp_path / "x.e"), str(tmp_path / "out.npz"), "--reference_mesh", str(tmp_path / "w.e"), "--smoother_niter", "200",
+                 "--smoother_tol", "1e-4", "--log", str(tmp_path / "log.txt")])
+    out = np.load(tmp_path / "out.npz")["coords"]
+    assert np.array_equal(out[:, fixed == 1], W[:, fixed == 1])           # skin did not move
+    assert np.max(np.abs(out - W)) < 0.05 * np.max(np.abs(X - W))          # interior went back to the reference mesh
+    assert len(open(tmp_path / "log.txt").read().splitlines()) > 2

@@ -19,6 +19,9 @@ def run(kind, nele, eps, reps=5):
     c.commit()
     c.upload("coordinates", X); c.upload("coordinates_N", X); c.upload("coordinates_NM1", W)
     c.set_option("cache_metric", 0)
+    if os.environ.get("QB_VARIANT"):
+        vm, vg = os.environ["QB_VARIANT"].split(",")
+        c.set_option("variant_metric_corners", int(vm)); c.set_option("variant_grad_corners", int(vg))
     ne, nnod = c.num_elements_local, c.num_nodes_local
     print(f"--- {kind} {nele}^3: {ne} elems, {nnod} nodes, setup {time.time()-t0:.1f}s")
     s = 1e-3 / nele * np.random.default_rng(0).standard_normal((3, nnod)); c.upload("cg_s", s)
