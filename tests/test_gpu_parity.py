@@ -350,3 +350,54 @@ def test_anisotropic_odd_sized_mesh(kind, variant):
     assert rel(g.download("coordinates"), o.download("coordinates")) < 1e-9
     g.set_option("variant_metric_corners", 2)
     g.set_option("variant_grad_corners", 2)
+
+
+def _outcome(ctx, niter, tol):
+    """(status, payload): run_algorithm result or the error text the reference would throw."""
+    try:
+        st = ctx.run_algorithm(niter, tol)
+        return "ok", (st.stage, st.iter, int(st.num_invalid), st.global_metric)
+    except Exception as ex:  # SmootherError on both backends
+        msg = str(ex)
+        for key in ("bad sDotGrad", "can't reduce metric", "Invalid elements", "bad alpha"):
+            if key in msg:
+                return "throw", key
+        return "throw", msg
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_edge_cases_behave_like_the_reference(kind):
+    """Smallest meshes, nothing free to move, already-optimal mesh: same results or the same reference error."""
+    # (a) one cell (all 8 nodes on the boundary => everything fixed): gradient zero, line search has no descent direction
+    X, W = meshes.perturbed_coords(1, 0.0)
+    g = meshes.build(pb.api, kind, 1, X, W, True)
+    o = meshes.build(oracle, kind, 1, X, W, True, {"real_is_double": 1})
+    (mg, ng), (mo, no) = g.total_metric(1, 0.0), o.total_metric(1, 0.0)
+    assert ng == no == 0 and abs(mg - mo) < 1e-13  # optimal mesh: the metric is rounding noise around 0 (terms are O(volume))
+    g.get_gradient(1)
+    assert not g.download("cg_g").any()
+    assert _outcome(g, 3, 1e-4) == _outcome(o, 3, 1e-4)
+    # (b) 2x2x2 cells, one free node, unperturbed (already optimal: metric 0 up to rounding)
+    X, W = meshes.perturbed_coords(2, 0.0)
+    g = meshes.build(pb.api, kind, 2, X, W, True)
+    o = meshes.build(oracle, kind, 2, X, W, True, {"real_is_double": 1})
+    mg, ng = g.total_metric(1, 0.0)
+    mo, no = o.total_metric(1, 0.0)
+    assert ng == no == 0 and abs(mg - mo) < 1e-13
+    # (c) 2x2x2 cells with the single free node displaced: one CG iteration per stage brings it (almost) back.
+    # (More iterations reach metric ~1e-15, where Armijo decisions are rounding noise: the oracle then succeeds with
+    # Double = long double and throws "can't reduce metric" with Double = double - the reference is equally fragile.)
+    X2 = X.copy()
+    X2[:, 13] += np.array([0.11, -0.07, 0.05])
+    g = meshes.build(pb.api, kind, 2, X2, W, True)
+    o = meshes.build(oracle, kind, 2, X2, W, True, {"real_is_double": 1})
+    rg, ro = _outcome(g, 1, 0.0), _outcome(o, 1, 0.0)
+    assert rg[0] == ro[0] == "ok" and rg[1][:3] == ro[1][:3]
+    assert np.max(np.abs(g.download("coordinates") - o.download("coordinates"))) < 1e-9
+    assert np.max(np.abs(g.download("coordinates")[:, 13] - W[:, 13])) < 0.2 * np.max(np.abs(X2[:, 13] - W[:, 13]))
+    # (d) no fixed nodes at all (the reference KAT configuration): gradient still sums to ~0 per component (translation invariance)
+    X, W = meshes.perturbed_coords(5, 0.3)
+    g = meshes.build(pb.api, kind, 5, X, W, False)
+    g.get_gradient(1)
+    gg = g.download("cg_g")
+    assert np.all(np.abs(gg.sum(axis=1)) <= 1e-10 * np.abs(gg).sum(axis=1))
