@@ -27,6 +27,8 @@ def main():
     mode = sys.argv[3] if len(sys.argv) > 3 else "hex8"
     if mode == "sgrid":
         return main_sgrid(rank, world, local, procs, n, cells, h, niter, eps)
+    if mode == "tet4":
+        return main_tet4(rank, world, local, niter, eps)
 
     lm = part.box_local_mesh(cells, procs, rank)
     W = lm.global_lattice_coords(h)
@@ -102,6 +104,66 @@ def nccl_uid(rank):
     uid = uid.cuda()
     dist.broadcast(uid, 0)
     return uid.cpu().numpy().tobytes()
+
+
+def main_tet4(rank, world, local, niter, eps):
+    """BASELINE config 4 at test size: tet4 mesh from a subdivided cube, deterministic RCB on element centroids,
+    one aura layer, owner->ghost exchange; compared with the same mesh on one GPU."""
+    from percept_b200 import fixtures as fx
+    n = 12
+    nn = n + 1
+    conn = fx.tet4_from_hex8(fx.hex8_connectivity(n)).astype(np.int64)
+    W = fx.cube(nn)
+    fixed = fx.cube_boundary_mask(nn)
+    gid_all = np.arange(nn ** 3)
+    X = part.perturb_by_global_id(W, gid_all, fixed, eps / n, seed=4)
+    er = part.rcb(W.T[conn].mean(axis=1), world)
+    lm = part.local_mesh(conn, er, rank, world, fixed)
+    c = pb.create(local)
+    c.set_unstructured(pb.TET4, lm.nnodes, lm.conn, lm.elem_owned, lm.node_owned)
+    c.set_fixed_mask(lm.node_on_global_boundary)
+    c.commit()
+    c.comm_init(nccl_uid(rank), rank, world)
+    c.set_halo(lm.nb_ranks, lm.send_off, lm.send_nodes, lm.recv_off, lm.recv_nodes)
+    for f, v in (("coordinates", X[:, lm.node_gid]), ("coordinates_N", X[:, lm.node_gid]), ("coordinates_NM1", W[:, lm.node_gid])):
+        c.upload(f, np.ascontiguousarray(v))
+    m1, n1 = c.metric_and_gradient(1)
+    g_local = c.download("cg_g")
+    st = c.run_algorithm(niter, 0.0)
+    x_local = c.download("coordinates")
+    ngl = nn ** 3
+
+    def assemble(f):
+        full = torch.zeros((3, ngl), dtype=torch.float64, device="cuda")
+        o = lm.node_owned == 1
+        full[:, torch.from_numpy(lm.node_gid[o]).cuda()] = torch.from_numpy(np.ascontiguousarray(f[:, o])).cuda()
+        dist.all_reduce(full)
+        return full.cpu().numpy()
+    xg, gg = assemble(x_local), assemble(g_local)
+    ghost_ok = np.array_equal(xg[:, lm.node_gid], x_local)
+    if rank == 0:
+        s = pb.create(local)
+        s.set_unstructured(pb.TET4, ngl, conn.astype(np.int32))
+        s.set_fixed_mask(fixed)
+        s.commit()
+        for f, v in (("coordinates", X), ("coordinates_N", X), ("coordinates_NM1", W)):
+            s.upload(f, v)
+        ms, ns = s.metric_and_gradient(1)
+        gs = s.download("cg_g")
+        ss = s.run_algorithm(niter, 0.0)
+        xs = s.download("coordinates")
+        rel = lambda a, b: np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+        res = {"metric_rel": abs(m1 - ms) / abs(ms), "ninv": (n1, ns), "grad_rel": rel(gg, gs), "coord_rel": rel(xg, xs),
+               "final_metric_rel": abs(st.global_metric - ss.global_metric) / abs(ss.global_metric), "ghost_ok": bool(ghost_ok),
+               "parts": np.bincount(er).tolist()}
+        print("MGRESULT", res, flush=True)
+        assert n1 == ns and res["metric_rel"] < 1e-12 and res["grad_rel"] < 1e-12, res
+        assert res["coord_rel"] < 1e-9 and res["final_metric_rel"] < 1e-9, res
+        assert st.num_nodes == ss.num_nodes == ngl
+    assert ghost_ok
+    dist.barrier()
+    dist.destroy_process_group()
+    print("MGOK", rank, flush=True)
 
 
 def main_sgrid(rank, world, local, procs, n, cells, h, niter, eps):

@@ -14,15 +14,16 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("mode", ["hex8", "sgrid"])
+@pytest.mark.parametrize("mode", ["hex8", "sgrid", "tet4"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_partitioned_smoothing_matches_single_gpu(world, mode):
     """hex8: geometric box partition + aura layer + owner->ghost cg_s exchange; sgrid: one structured block per GPU with
-    interface-node sums (the multi-block == single-block property of SGridSmootherMultiBlockvsSingleBlock.cpp)."""
+    interface-node sums (the multi-block == single-block property of SGridSmootherMultiBlockvsSingleBlock.cpp); tet4:
+    deterministic RCB on element centroids (BASELINE config 4 at test size)."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29740 + world + (10 if mode == "sgrid" else 0)), os.path.join(ROOT, "tests", "mg_worker.py"),
+           "--master-port", str(29740 + world + {"hex8": 0, "sgrid": 10, "tet4": 20}[mode]), os.path.join(ROOT, "tests", "mg_worker.py"),
            "6", "0.3", mode]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
