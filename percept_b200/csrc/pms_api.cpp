@@ -16,7 +16,9 @@
 #include <cstring>
 #include <fstream>
 #include <iomanip>
+#include <functional>
 #include <numeric>
+#include <thread>
 
 #include "pms_ctx.h"
 
@@ -290,6 +292,244 @@ void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// brick tables (host): Morton order of reference-mesh centroids, 128 elements per brick, brick-local node CSR,
+// brick-surface partial-sum plan.  One-time cost per mesh (a few seconds at 16.8 M hexes, multi-threaded).
+// ---------------------------------------------------------------------------------------------
+static inline uint64_t spread21(uint64_t v) {
+  v &= 0x1fffff;
+  v = (v | v << 32) & 0x1f00000000ffffULL;
+  v = (v | v << 16) & 0x1f0000ff0000ffULL;
+  v = (v | v << 8) & 0x100f00f00f00f00fULL;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+  v = (v | v << 2) & 0x1249249249249249ULL;
+  return v;
+}
+
+void build_bricks(pms_ctx* c) {
+  if (c->structured || c->topo != 8) {
+    c->bricks_failed = true;
+    return;
+  }
+  for (void* p : c->brick_allocs) cudaFree(p);
+  c->brick_allocs.clear();
+  const long long N = c->N, E = c->E;
+  const int BS = 128;
+  DField& W = c->field("coordinates_NM1");
+  std::vector<double> w((size_t)3 * N);
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 3; k++) PMS_CUDA(cudaMemcpy(w.data() + (size_t)k * N, W.d + (size_t)k * c->Npad, N * sizeof(double), cudaMemcpyDeviceToHost));
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (int k = 0; k < 3; k++)
+    for (long long n = 0; n < N; n++) {
+      lo[k] = std::min(lo[k], w[(size_t)k * N + n]);
+      hi[k] = std::max(hi[k], w[(size_t)k * N + n]);
+    }
+  double ext = 0;
+  for (int k = 0; k < 3; k++) ext = std::max(ext, hi[k] - lo[k]);
+  if (!(ext > 0) || !std::isfinite(ext)) {
+    c->bricks_failed = true;  // reference mesh not uploaded yet / degenerate: keep the scratch path
+    return;
+  }
+  const unsigned nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  auto parallel_for = [&](long long n, const std::function<void(long long, long long)>& fn) {
+    std::vector<std::thread> th;
+    const long long chunk = (n + nthreads - 1) / nthreads;
+    for (unsigned t = 0; t < nthreads; t++) {
+      const long long a = t * chunk, b = std::min(n, a + chunk);
+      if (a < b) th.emplace_back(fn, a, b);
+    }
+    for (auto& x : th) x.join();
+  };
+  std::vector<std::pair<uint64_t, int32_t>> order(E);
+  const double sc = 2097151.0 / ext;
+  parallel_for(E, [&](long long a, long long b) {
+    for (long long e = a; e < b; e++) {
+      double cx[3] = {0, 0, 0};
+      for (int v = 0; v < 8; v++) {
+        const long long n = c->h_conn[(size_t)e * 8 + v];
+        for (int k = 0; k < 3; k++) cx[k] += w[(size_t)k * N + n];
+      }
+      uint64_t key = 0;
+      for (int k = 0; k < 3; k++) key |= spread21((uint64_t)std::min(2097151.0, std::max(0.0, (cx[k] * 0.125 - lo[k]) * sc))) << k;
+      order[e] = {key, (int32_t)e};
+    }
+  });
+  std::sort(order.begin(), order.end());
+  // greedy cut of the Morton sequence: 128 elements per brick, fewer when the brick would touch too many nodes
+  const int NODE_CAP = pmsk::BRICK_MAX_NODES - 32;  // slack of 512 B in the gather-table buffer for valence > 8
+  std::vector<long long> bstart{0};
+  {
+    std::vector<int32_t> stamp(N, -1);
+    int ne = 0, nn = 0;
+    for (long long s = 0; s < E; s++) {
+      const int32_t e = order[s].second;
+      int fresh = 0;
+      const int32_t id = (int32_t)(bstart.size() - 1);
+      for (int v = 0; v < 8; v++) fresh += stamp[c->h_conn[(size_t)e * 8 + v]] != id;  // (repeated nodes over-count: harmless)
+      if (ne == BS || nn + fresh > NODE_CAP) {
+        bstart.push_back(s);
+        ne = nn = 0;
+      }
+      const int32_t id2 = (int32_t)(bstart.size() - 1);
+      for (int v = 0; v < 8; v++) {
+        int32_t& st = stamp[c->h_conn[(size_t)e * 8 + v]];
+        if (st != id2) {
+          st = id2;
+          nn++;
+        }
+      }
+      ne++;
+    }
+    bstart.push_back(E);
+  }
+  const long long nb = (long long)bstart.size() - 1;
+  auto pad = [](long long v, long long m) { return (v + m - 1) / m * m; };
+  static const int PERM[8] = {0, 1, 3, 2, 4, 5, 7, 6};  // structured position <-> Exodus local node (an involution)
+  // per brick: distinct nodes (ascending), completeness, contributions in ascending (element id, local node) order
+  struct BrickTmp {
+    std::vector<int32_t> node, cnt;
+    std::vector<uint8_t> complete;
+    std::vector<uint16_t> gent;
+  };
+  std::vector<BrickTmp> tmp(nb);
+  std::vector<uint16_t> ctab((size_t)nb * (pmsk::BRICK_CTAB_BYTES / 2), 0);
+  parallel_for(nb, [&](long long a, long long b) {
+    struct Ent {
+      int32_t node, elem;
+      uint16_t ta;
+    };
+    std::vector<Ent> ents;
+    for (long long br = a; br < b; br++) {
+      ents.clear();
+      uint16_t* lconn = ctab.data() + (size_t)br * (pmsk::BRICK_CTAB_BYTES / 2);
+      int32_t* belem = reinterpret_cast<int32_t*>(lconn + BS * 8);
+      for (int t = 0; t < BS; t++) {
+        const long long s = bstart[br] + t;
+        const int32_t e = s < bstart[br + 1] ? order[s].second : -1;
+        belem[t] = e;
+        if (e < 0) continue;
+        for (int v = 0; v < 8; v++) ents.push_back({c->h_conn[(size_t)e * 8 + v], e, (uint16_t)(t * 8 + v)});
+      }
+      std::sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) {
+        if (x.node != y.node) return x.node < y.node;
+        if (x.elem != y.elem) return x.elem < y.elem;
+        return (x.ta & 7) < (y.ta & 7);
+      });
+      BrickTmp& T = tmp[br];
+      for (size_t i = 0; i < ents.size();) {
+        size_t j = i;
+        const int lj = (int)T.node.size();
+        while (j < ents.size() && ents[j].node == ents[i].node) {
+          const int t = ents[j].ta >> 3, p = PERM[ents[j].ta & 7];
+          T.gent.push_back((uint16_t)(t * 8 + p));
+          lconn[t * 8 + p] = (uint16_t)lj;
+          j++;
+        }
+        const int32_t nd = ents[i].node;
+        T.node.push_back(nd);
+        T.cnt.push_back((int32_t)(j - i));
+        T.complete.push_back((int64_t)(j - i) == c->h_csr_ptr[nd + 1] - c->h_csr_ptr[nd]);
+        i = j;
+      }
+    }
+  });
+  // blob sizes / partial numbering (serial prefix), then fill in parallel
+  std::vector<int32_t> goff(nb + 1, 0), part0(nb + 1, 0), bnn(nb, 0), novf(nb, 0);
+  std::vector<int32_t> pcount(N, 0);
+  for (long long br = 0; br < nb; br++) {
+    const BrickTmp& T = tmp[br];
+    const long long nn = (long long)T.node.size();
+    int ov = 0, np = 0;
+    for (size_t j = 0; j < T.node.size(); j++) {
+      if (T.cnt[j] > 8) ov += 2 + (T.cnt[j] - 8);
+      if (!T.complete[j]) {
+        np++;
+        pcount[T.node[j]]++;
+      }
+    }
+    const long long bytes = 16 + 8 * pad(nn, 4) + 16 * nn + 2 * pad(ov, 8);
+    if (nn > pmsk::BRICK_MAX_NODES || bytes > pmsk::BRICK_GTAB_BYTES || (long long)goff[br] + bytes / 16 >= (1ll << 31) ||
+        (long long)part0[br] + np >= (1ll << 31)) {
+      c->bricks_failed = true;  // (e.g. a node shared by hundreds of elements): keep the scratch path
+      return;
+    }
+    bnn[br] = (int32_t)nn;
+    novf[br] = ov;
+    goff[br + 1] = goff[br] + (int32_t)(bytes / 16);
+    part0[br + 1] = part0[br] + np;
+  }
+  const long long npart = part0[nb];
+  // combine plan: nodes with partials, partial indices in ascending brick order
+  std::vector<int32_t> comb_node, comb_ptr{0}, comb_slot(N, -1);
+  for (long long n = 0; n < N; n++)
+    if (pcount[n] > 0) {
+      comb_slot[n] = (int32_t)comb_node.size();
+      comb_node.push_back((int32_t)n);
+      comb_ptr.push_back(comb_ptr.back() + pcount[n]);
+    }
+  std::vector<int32_t> comb_ent(npart), fill(comb_ptr.begin(), comb_ptr.end() - 1);
+  for (long long br = 0; br < nb; br++) {
+    const BrickTmp& T = tmp[br];
+    int32_t q = part0[br];
+    for (size_t j = 0; j < T.node.size(); j++)
+      if (!T.complete[j]) comb_ent[fill[comb_slot[T.node[j]]]++] = q++;
+  }
+  std::vector<int32_t> gtab((size_t)goff[nb] * 4, 0);
+  const bool have_owned = !c->h_node_owned.empty();
+  parallel_for(nb, [&](long long a, long long b) {
+    for (long long br = a; br < b; br++) {
+      const BrickTmp& T = tmp[br];
+      const int nn = (int)T.node.size();
+      int32_t* blob = gtab.data() + (size_t)goff[br] * 4;
+      blob[0] = nn;
+      blob[1] = novf[br];
+      int32_t* tnode = blob + 4;
+      int32_t* tdst = tnode + pad(nn, 4);
+      uint16_t* tell = reinterpret_cast<uint16_t*>(tdst + pad(nn, 4));
+      uint16_t* tovf = tell + (size_t)nn * 8;
+      int32_t q = part0[br];
+      int off = 0, o = 0;
+      for (int j = 0; j < nn; j++) {
+        const int32_t nd = T.node[j];
+        tnode[j] = nd;
+        for (int k = 0; k < 8; k++) tell[j * 8 + k] = k < T.cnt[j] ? T.gent[off + k] : (uint16_t)0xffff;
+        if (T.cnt[j] > 8) {
+          tovf[o++] = (uint16_t)j;
+          tovf[o++] = (uint16_t)(T.cnt[j] - 8);
+          for (int k = 8; k < T.cnt[j]; k++) tovf[o++] = T.gent[off + k];
+        }
+        off += T.cnt[j];
+        if (T.complete[j])
+          tdst[j] = (c->h_fixed[nd] || (have_owned && !c->h_node_owned[nd])) ? -2 : -1;
+        else
+          tdst[j] = q++;
+      }
+    }
+  });
+
+  pmsk::BrickDev& B = c->bricks;
+  auto up = [&](auto& v) {
+    auto* p = dupload(v);
+    c->brick_allocs.push_back((void*)p);
+    return p;
+  };
+  B.nbricks = nb;
+  B.ctab = reinterpret_cast<const uint4*>(up(ctab));
+  B.bnn = up(bnn);
+  B.goff = up(goff);
+  B.gtab = reinterpret_cast<const uint4*>(up(gtab));
+  B.npartial = std::max<long long>(npart, 1);
+  B.partial = dalloc<double>((size_t)3 * B.npartial);
+  c->brick_allocs.push_back((void*)B.partial);
+  B.ncomb = (long long)comb_node.size();
+  B.comb_node = up(comb_node);
+  B.comb_ptr = up(comb_ptr);
+  B.comb_ent = up(comb_ent);
+  c->bricks_built = true;
+  c->bricks_wv = W.version;
+}
+
 void ensure_eg(pms_ctx* c) {
   if (!c->d_eg) c->d_eg = dalloc<double>((size_t)3 * (c->topo == 4 ? 4 : 8) * c->Epad);
 }
@@ -312,6 +552,19 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write
       if (!fused_ok) {
         c->launches--;
         c->fam_launches[FAM_GRADIENT]--;
+      }
+    }
+  }
+  if (!fused_ok && !c->structured && c->topo == 8 && c->var_grad == 4 && !c->strict_fp && !c->keep_elem && use_ref) {
+    if (!c->bricks_built && !c->bricks_failed) build_bricks(c);
+    if (c->bricks_built) {
+      Timed t(c, FAM_GRADIENT, 2);
+      fused_ok = c->L->grad_bricks(c->stream, c->dev_blocks[0], c->bricks, stage, X.d, W.d, c->Npad, c->d_fixed, c->d_node_owned,
+                                   G.d, write_r ? Rr.d : nullptr, c->R, 0, nullptr, nullptr);
+      check_launch(c, "grad_bricks");
+      if (!fused_ok) {
+        c->launches -= 2;
+        c->fam_launches[FAM_GRADIENT] -= 2;
       }
     }
   }
@@ -756,6 +1009,7 @@ void pms_destroy(pms_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->fields) cudaFree(kv.second.d);
+    for (void* p : c->brick_allocs) cudaFree(p);
     void* ptrs[] = {c->d_conn,      c->d_fixed,     c->d_node_owned, c->d_elem_owned, c->d_dotmask,  c->d_elem_bits,
                     c->d_csr_ptr,   c->d_csr_ent,   c->d_grp_ptr,    c->d_grp_nodes,  c->d_eg,       c->d_elem_metric,
                     c->d_elem_flag, c->R.partial_d, c->R.partial_u,  c->R.ticket,     c->R.out_d,    c->R.out_u,
@@ -898,6 +1152,7 @@ int pms_set_fixed_mask(pms_ctx* c, const uint8_t* fixed) {
   if (c->committed) {
     PMS_CUDA(cudaMemcpy(c->d_fixed, c->h_fixed.data(), n, cudaMemcpyHostToDevice));
     rebuild_skip_mask(c);
+    c->bricks_built = false;  // the brick tables bake the fixed mask in
     for (auto& mb : c->dev_blocks) c->L->elem_fixed_bits(c->stream, mb, c->d_fixed, c->d_elem_bits);
     check_launch(c, "elem_fixed_bits");
     invalidate_cache(c);

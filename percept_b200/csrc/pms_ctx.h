@@ -76,6 +76,11 @@ struct pms_ctx {
   int64_t *d_grp_ptr = nullptr, *d_grp_nodes = nullptr;
   long long n_groups = 0;
   double* d_eg = nullptr;  // element-gradient scratch [3*npe][Epad]
+  // brick tables of the scratch-free hex8 gradient (built lazily from the reference-mesh centroids)
+  pmsk::BrickDev bricks{};
+  bool bricks_built = false, bricks_failed = false;
+  uint64_t bricks_wv = 0;
+  std::vector<void*> brick_allocs;
   double* d_elem_metric = nullptr;
   int32_t* d_elem_flag = nullptr;
 

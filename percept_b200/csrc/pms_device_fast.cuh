@@ -66,6 +66,14 @@ struct SmemVerts {  // vertices read in place from a thread-private shared-memor
   }
 };
 
+template <int NN>
+struct IdxVerts {  // vertices of a brick staged once per distinct node: base[r*NN + local node index]
+  const double* base;
+  const int (&off)[8];  // local node index of structured position p
+  PMS_DI IdxVerts(const double* b, const int (&o)[8]) : base(b), off(o) {}
+  PMS_DI double operator()(int p, int r) const { return base[r * NN + off[p]]; }
+};
+
 // canonical edge along axis AX touching corner c (vertices in structured numbering node = i+2j+4k)
 template <int AX, class V>
 PMS_DI void corner_edge(const V& v, int c, double (&e)[3]) {

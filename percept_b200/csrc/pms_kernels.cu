@@ -709,6 +709,239 @@ static void launch_elem_pipe(cudaStream_t st, const MeshDev& m, const double* x,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Scratch-free hex8 gradient over bricks (default build).  The 192 B/hex element->node scratch of the two-pass scheme
+// costs 5x the algorithmic HBM traffic and a 0.6 ms gather.  Here elements are visited in Morton order of their
+// reference-mesh centroids, 128 per CTA iteration ("brick", a compact 8x4x4-like clump of ~225 distinct nodes):
+//   stage   the brick's DISTINCT nodes (x and reference w) are cp.async'ed once into shared memory, one brick ahead
+//           (~11 8-byte copies per thread instead of 48), together with the brick's tables;
+//   compute one thread per hex reads its 8 vertices through brick-local indices and evaluates metric + 24 derivatives
+//           exactly as k_elem_pipe does, then drops the 24 contributions into a shared-memory exchange column;
+//   gather  one barrier later (at the top of the next iteration) thread j sums node j's contributions in ascending
+//           (element id, local node) order from an 8-wide ELL row.  Nodes whose adjacent elements all lie in the
+//           brick go straight to cg_g / cg_r; brick-surface nodes write one partial, and k_brick_combine adds a node's
+//           partials in ascending brick id.
+// Deterministic, no atomics, no redundant corner evaluations, one __syncthreads per brick.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
+constexpr int BR_NN = BRICK_MAX_NODES;
+constexpr int BR_XS = 6 * BR_NN;   // doubles per vertex staging buffer: [x|w][3][BR_NN]
+constexpr int BR_EX = 24 * NTP;    // doubles per exchange buffer: [(p*3+r)][NTP]
+constexpr size_t BRICK_SMEM = (size_t)2 * (BR_XS + BR_EX) * sizeof(double) + 2 * BRICK_CTAB_BYTES + 2 * BRICK_GTAB_BYTES;
+
+template <int STAGE>
+__global__ void __launch_bounds__(NTP, 2) k_brick_grad(const MeshDev m, const BrickDev B, const double* __restrict__ x,
+                                                       const double* __restrict__ w, const long long stride,
+                                                       double* __restrict__ g, double* __restrict__ rout, const Reduce R,
+                                                       const int slot) {
+  static_assert(NTP == BRICK_ELEMS, "one thread per brick element");
+  extern __shared__ double sm[];
+  double* const xs = sm;                    // [2][BR_XS]
+  double* const exb = sm + 2 * BR_XS;       // [2][BR_EX]
+  char* const ctb = reinterpret_cast<char*>(exb + 2 * BR_EX);  // [2][BRICK_CTAB_BYTES]
+  char* const gtb = ctb + 2 * BRICK_CTAB_BYTES;                // [2][BRICK_GTAB_BYTES]
+  const int tid = threadIdx.x;
+  double val[1] = {0.0};
+  unsigned long long inv = 0;
+  const long long nbricks = B.nbricks, gstep = gridDim.x;
+
+  // metadata registers: node ids this thread stages for the next brick, gather-table range of the current one
+  int nid[3] = {0, 0, 0}, nn_s = 0, go0 = 0, go1 = 0;
+  auto load_meta = [&](long long b_stage, long long b_gt) {
+    nn_s = 0;
+    go0 = go1 = 0;
+    if (b_gt < nbricks) {
+      go0 = __ldg(&B.goff[b_gt]);
+      go1 = __ldg(&B.goff[b_gt + 1]);
+    }
+    if (b_stage < nbricks) {
+      nn_s = __ldg(&B.bnn[b_stage]);
+      const int* tn = reinterpret_cast<const int*>(B.gtab + __ldg(&B.goff[b_stage])) + 4;
+#pragma unroll
+      for (int q = 0; q < 3; q++) nid[q] = (tid + q * NTP < nn_s) ? __ldg(&tn[tid + q * NTP]) : 0;
+    }
+  };
+  auto issue = [&](long long b_stage, int sbuf, int gbuf) {
+    if (b_stage < nbricks) {
+      double* xb = xs + (size_t)sbuf * BR_XS;
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const int j = tid + q * NTP;
+        if (j < nn_s) {
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            cp_async8(xb + r * BR_NN + j, &x[r * stride + nid[q]]);
+            cp_async8(xb + (3 + r) * BR_NN + j, &w[r * stride + nid[q]]);
+          }
+        }
+      }
+      char* cb = ctb + (size_t)sbuf * BRICK_CTAB_BYTES;
+      const uint4* src = B.ctab + b_stage * (BRICK_CTAB_BYTES / 16);
+      cp_async16(cb + tid * 16, src + tid);
+      if (tid < 32) cp_async16(cb + 2048 + tid * 16, src + 128 + tid);
+    }
+    char* gb = gtb + (size_t)gbuf * BRICK_GTAB_BYTES;
+    for (int i = go0 + tid; i < go1; i += NTP) cp_async16(gb + (size_t)(i - go0) * 16, &B.gtab[i]);
+    cp_async_commit();
+  };
+  auto gather = [&](int pb) {
+    const double* ex = exb + (size_t)pb * BR_EX;  // ex[(p*3+r)*NTP + t]
+    const int* T = reinterpret_cast<const int*>(gtb + (size_t)pb * BRICK_GTAB_BYTES);
+    const int nn = T[0], novf = T[1], nn4 = (nn + 3) & ~3;
+    const int* tnode = T + 4;
+    const int* tdst = tnode + nn4;
+    const uint4* tell = reinterpret_cast<const uint4*>(tdst + nn4);
+    for (int j = tid; j < nn; j += NTP) {
+      const int node = tnode[j], dst = tdst[j];
+      const uint4 q = tell[j];
+      const unsigned qq[4] = {q.x, q.y, q.z, q.w};
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const unsigned ent = (qq[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+        const bool on = ent != 0xffffu;
+        const unsigned e2 = on ? ent : 0u;
+        const double* col = ex + (e2 & 7u) * 3 * NTP + (e2 >> 3);
+        const double v0 = col[0], v1 = col[NTP], v2 = col[2 * NTP];
+        s0 += on ? v0 : 0.0;
+        s1 += on ? v1 : 0.0;
+        s2 += on ? v2 : 0.0;
+      }
+      if (novf > 0) {  // node shared by more than 8 elements of the brick (irregular meshes)
+        const uint16_t* ov = reinterpret_cast<const uint16_t*>(tell + nn);
+        for (int i = 0; i < novf;) {
+          const int jj = ov[i], cnt = ov[i + 1];
+          if (jj == j)
+            for (int k = 0; k < cnt; k++) {
+              const unsigned ent = ov[i + 2 + k];
+              const double* col = ex + (ent & 7u) * 3 * NTP + (ent >> 3);
+              s0 += col[0];
+              s1 += col[NTP];
+              s2 += col[2 * NTP];
+            }
+          i += 2 + cnt;
+        }
+      }
+      if (dst < 0) {
+        if (dst == -2) s0 = s1 = s2 = 0.0;  // fixed or not owned (Def.hpp:1226-1244)
+        g[node] = s0;
+        g[stride + node] = s1;
+        g[2 * stride + node] = s2;
+        if (rout) {
+          rout[node] = s0;
+          rout[stride + node] = s1;
+          rout[2 * stride + node] = s2;
+        }
+      } else {
+        B.partial[dst] = s0;
+        B.partial[B.npartial + dst] = s1;
+        B.partial[2 * B.npartial + dst] = s2;
+      }
+    }
+  };
+
+  long long brick = blockIdx.x;
+  load_meta(brick, nbricks);
+  issue(brick, 0, 0);  // vertices + compute table of the first brick (no gather table yet: go0 == go1)
+  load_meta(brick + gstep, brick);
+  int it = 0;
+  for (; brick < nbricks; brick += gstep, it++) {
+    const int cur = it & 1;
+    cp_async_wait_all();
+    __syncthreads();  // staged vertices/tables of this brick and the exchange column of the previous one are complete
+    if (it > 0) gather(cur ^ 1);
+    issue(brick + gstep, cur ^ 1, cur);  // next brick's vertices; this brick's gather table (needed next iteration)
+    load_meta(brick + 2 * gstep, brick + gstep);
+
+    const char* cb = ctb + (size_t)cur * BRICK_CTAB_BYTES;
+    const uint4 lc = *reinterpret_cast<const uint4*>(cb + tid * 16);
+    const int e_cur = reinterpret_cast<const int*>(cb + 2048)[tid];
+    const int off[8] = {(int)(lc.x & 0xffffu), (int)(lc.x >> 16), (int)(lc.y & 0xffffu), (int)(lc.y >> 16),
+                        (int)(lc.z & 0xffffu), (int)(lc.z >> 16), (int)(lc.w & 0xffffu), (int)(lc.w >> 16)};
+    double grad[8][3];
+    bool use = false;
+    if (e_cur >= 0) {
+      const double* xb = xs + (size_t)cur * BR_XS;
+      const IdxVerts<BR_NN> VC(xb, off), VO(xb + 3 * BR_NN, off);
+      bool valid;
+      const double mm = hex_metric_fast_v<STAGE, true>(VC, VO, valid, grad);
+      use = valid || STAGE == 0;  // Def.hpp:1219
+      bool counted = true;
+      if (m.elem_owned) counted = m.elem_owned[e_cur] != 0;
+      if (counted) {
+        val[0] += mm;
+        inv += valid ? 0 : 1;
+      }
+    }
+    double* exw = exb + (size_t)cur * BR_EX + tid;
+#pragma unroll
+    for (int p = 0; p < 8; p++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) exw[(p * 3 + r) * NTP] = use ? grad[p][r] : 0.0;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (it > 0) gather((it - 1) & 1);
+  grid_reduce<OpSum, 1, true>(val, inv, R, slot);
+}
+
+__global__ void __launch_bounds__(NT) k_brick_combine(const BrickDev B, const uint8_t* __restrict__ fixed,
+                                                      const uint8_t* __restrict__ owned, double* __restrict__ g,
+                                                      double* __restrict__ rout, const long long stride) {
+  const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+  if (i >= B.ncomb) return;
+  const int node = B.comb_node[i];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  if (!(fixed[node] || (owned && !owned[node]))) {
+    for (int p = B.comb_ptr[i]; p < B.comb_ptr[i + 1]; p++) {
+      const long long q = B.comb_ent[p];
+      s0 += B.partial[q];
+      s1 += B.partial[B.npartial + q];
+      s2 += B.partial[2 * B.npartial + q];
+    }
+  }
+  g[node] = s0;
+  g[stride + node] = s1;
+  g[2 * stride + node] = s2;
+  if (rout) {
+    rout[node] = s0;
+    rout[stride + node] = s1;
+    rout[2 * stride + node] = s2;
+  }
+}
+
+static bool launch_grad_bricks(cudaStream_t st, const MeshDev& m, const BrickDev& B, int stage, const double* x, const double* w,
+                               long long stride, const uint8_t* fixed, const uint8_t* owned, double* g, double* rout,
+                               const Reduce& R, int slot, double* em, int32_t* ef) {
+  if (STRICT || m.kind != KIND_HEX8) return false;
+  const size_t smem = BRICK_SMEM;
+  static int blocks_per_sm[2] = {0, 0};
+  auto k0 = k_brick_grad<0>;
+  auto k1 = k_brick_grad<1>;
+  if (!blocks_per_sm[stage]) {
+    if (stage == 0) {
+      cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], k0, NTP, smem);
+    } else {
+      cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], k1, NTP, smem);
+    }
+    if (blocks_per_sm[stage] < 1) blocks_per_sm[stage] = 1;
+  }
+  const long long cap = 148LL * blocks_per_sm[stage];
+  const unsigned grid = (unsigned)(B.nbricks < cap ? (B.nbricks < 1 ? 1 : B.nbricks) : cap);
+  if (stage == 0)
+    k0<<<grid, NTP, smem, st>>>(m, B, x, w, stride, g, rout, R, slot);
+  else
+    k1<<<grid, NTP, smem, st>>>(m, B, x, w, stride, g, rout, R, slot);
+  if (B.ncomb > 0) k_brick_combine<<<(unsigned)((B.ncomb + NT - 1) / NT), NT, 0, st>>>(B, fixed, owned, g, rout, stride);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: total element metric at x + alpha*s          (total_element_metric.cpp:271-307, Def.hpp:330-388)
 // ------------------------------------------------------------------------------------------------
 template <int FL, int STAGE, bool USE_REF, bool WITH_S>
@@ -1341,7 +1574,7 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_group_sum, launch_axpby,         launch_axpbypgz,    launch_set,
                                       launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,
-                                      launch_unpack,    launch_elem_fixed_bits, launch_shared_sum};
+                                      launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_shared_sum};
 
 const Launchers* launchers() { return &g_launchers; }
 void set_variant(int metric_corners, int grad_corners) {

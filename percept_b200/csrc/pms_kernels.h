@@ -37,6 +37,33 @@ struct Reduce {  // scratch for deterministic two-level reductions (partials + l
   int max_blocks;
 };
 
+// Brick tables for the scratch-free unstructured hex8 gradient (built on the host from the reference-mesh centroids):
+// elements are Morton-sorted and cut into bricks of 128; slot = brick*128 + t.
+struct BrickDev {
+  long long nbricks;
+  // compute table, 2560 B per brick: uint16 lconn[128][8] (brick-local node index of structured position p of slot t)
+  // then int32 elem[128] (original element id, -1 = padding)
+  const uint4* ctab;
+  const int32_t* bnn;        // [nbricks] distinct nodes of the brick
+  // gather table, one 16-byte-aligned blob per brick:
+  //   int32 nn, novf, 0, 0 | int32 node[nn4] | int32 dst[nn4] | uint16 ell[nn][8] | uint16 ovf[pad8(novf)]
+  //   node: global ids ascending.  dst: -1 all adjacent elements inside the brick, free node -> cg_g; -2 same but
+  //   fixed / not owned -> 0; >= 0 index of this brick's partial sum.  ell: the node's first 8 contributions t*8+p in
+  //   ascending (element id, local node) order, 0xFFFF = none; ovf: [j, count, entries...] for the 9th onward.
+  const int32_t* goff;       // [nbricks+1] blob offsets in 16-byte units
+  const uint4* gtab;
+  double* partial;           // [3][npartial] brick-surface partial sums
+  long long npartial;
+  long long ncomb;           // nodes that have partials
+  const int32_t* comb_node;  // [ncomb]
+  const int32_t* comb_ptr;   // [ncomb+1]
+  const int32_t* comb_ent;   // partial indices, ascending brick id
+};
+constexpr int BRICK_ELEMS = 128;      // = NTP of the pipelined kernels
+constexpr int BRICK_MAX_NODES = 384;  // a brick is cut short when its distinct nodes would exceed this
+constexpr int BRICK_CTAB_BYTES = 2560;
+constexpr int BRICK_GTAB_BYTES = 16 + 8 * BRICK_MAX_NODES + 16 * BRICK_MAX_NODES;  // overflow shares the slack
+
 struct Launchers {
   // metric of (x + alpha*s on unfixed nodes) vs reference w; result: out_d[slot] = sum, out_u[slot] = #invalid.
   // s may be null (alpha = 0).  elem_metric/elem_flag optional.
@@ -88,6 +115,10 @@ struct Launchers {
   void (*unpack)(cudaStream_t, double* f, long long stride, int ncomp, const int32_t* nodes, long long count, const double* buf);
   // per-element bit mask of fixed vertices
   void (*elem_fixed_bits)(cudaStream_t, const MeshDev&, const uint8_t* fixed, uint8_t* bits);
+  // scratch-free hex8 gradient over bricks (default build only); returns false when unsupported
+  bool (*grad_bricks)(cudaStream_t, const MeshDev&, const BrickDev&, int stage, const double* x, const double* w,
+                      long long stride, const uint8_t* fixed, const uint8_t* node_owned, double* g, double* r_out,
+                      const Reduce&, int slot, double* elem_metric, int32_t* elem_flag);
   // cross-rank interface sum (structured block per GPU), ascending rank order
   void (*shared_sum)(cudaStream_t, long long nshared, const int32_t* nodes, const int64_t* ptr, const int64_t* ent_pos,
                      const int32_t* ent_cnt, const double* recvbuf, double* f, int ncomp, long long stride);
