@@ -422,7 +422,7 @@ void build_bricks(pms_ctx* c) {
         const int lj = (int)T.node.size();
         while (j < ents.size() && ents[j].node == ents[i].node) {
           const int t = ents[j].ta >> 3, p = PERM[ents[j].ta & 7];
-          T.gent.push_back((uint16_t)(t * 8 + p));
+          T.gent.push_back((uint16_t)(t * pmsk::BRICK_EX_STRIDE + p * 3));
           lconn[t * 8 + p] = (uint16_t)lj;
           j++;
         }
@@ -493,7 +493,7 @@ void build_bricks(pms_ctx* c) {
       for (int j = 0; j < nn; j++) {
         const int32_t nd = T.node[j];
         tnode[j] = nd;
-        for (int k = 0; k < 8; k++) tell[j * 8 + k] = k < T.cnt[j] ? T.gent[off + k] : (uint16_t)0xffff;
+        for (int k = 0; k < 8; k++) tell[j * 8 + k] = k < T.cnt[j] ? T.gent[off + k] : (uint16_t)pmsk::BRICK_EX_ZERO;
         if (T.cnt[j] > 8) {
           tovf[o++] = (uint16_t)j;
           tovf[o++] = (uint16_t)(T.cnt[j] - 8);
@@ -555,7 +555,7 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write
       }
     }
   }
-  if (!fused_ok && !c->structured && c->topo == 8 && c->var_grad == 4 && !c->strict_fp && !c->keep_elem && use_ref) {
+  if (!fused_ok && !c->structured && c->topo == 8 && c->var_grad >= 4 && !c->strict_fp && !c->keep_elem && use_ref) {
     if (!c->bricks_built && !c->bricks_failed) build_bricks(c);
     if (c->bricks_built) {
       Timed t(c, FAM_GRADIENT, 2);

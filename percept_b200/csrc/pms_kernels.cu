@@ -58,31 +58,44 @@ __device__ __forceinline__ int lin_tid() { return threadIdx.x + blockDim.x * (th
 __device__ __forceinline__ unsigned lin_bid() { return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); }
 __device__ __forceinline__ unsigned n_blocks() { return gridDim.x * gridDim.y * gridDim.z; }
 
-template <class OP>
+// BAR == 0: all threads of the block (__syncthreads).  BAR > 0: the first NTH threads only, on named barrier BAR
+// (warp-specialised kernels whose helper warps have already exited).
+template <int BAR, int NTH>
+__device__ __forceinline__ void red_sync() {
+  if (BAR == 0)
+    __syncthreads();
+  else
+    asm volatile("bar.sync %0, %1;" ::"r"(BAR), "r"(NTH) : "memory");
+}
+template <int BAR, int NTH>
+__device__ __forceinline__ int red_threads() { return BAR == 0 ? (int)(blockDim.x * blockDim.y * blockDim.z) : NTH; }
+
+template <class OP, int BAR = 0, int NTH = 0>
 __device__ __forceinline__ double block_reduce(double v, double* sm /*[NT/32]*/) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = OP::f(v, __shfl_down_sync(0xffffffffu, v, o));
   const int t = lin_tid();
-  __syncthreads();
+  red_sync<BAR, NTH>();
   if ((t & 31) == 0) sm[t >> 5] = v;
-  __syncthreads();
+  red_sync<BAR, NTH>();
   if (t < 32) {
-    const int nw = (blockDim.x * blockDim.y * blockDim.z) >> 5;
+    const int nw = red_threads<BAR, NTH>() >> 5;
     v = t < nw ? sm[t] : OP::id();
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) v = OP::f(v, __shfl_down_sync(0xffffffffu, v, o));
   }
   return v;  // valid in thread 0
 }
+template <int BAR = 0, int NTH = 0>
 __device__ __forceinline__ unsigned long long block_reduce_u(unsigned long long v, unsigned long long* sm) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   const int t = lin_tid();
-  __syncthreads();
+  red_sync<BAR, NTH>();
   if ((t & 31) == 0) sm[t >> 5] = v;
-  __syncthreads();
+  red_sync<BAR, NTH>();
   if (t < 32) {
-    const int nw = (blockDim.x * blockDim.y * blockDim.z) >> 5;
+    const int nw = red_threads<BAR, NTH>() >> 5;
     v = t < nw ? sm[t] : 0ull;
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -91,7 +104,7 @@ __device__ __forceinline__ unsigned long long block_reduce_u(unsigned long long 
 }
 
 // Block-level values -> global result.  NV double values reduced with OP, optionally one counter.
-template <class OP, int NV, bool WITH_U>
+template <class OP, int NV, bool WITH_U, int BAR = 0, int NTH = 0>
 __device__ __forceinline__ void grid_reduce(double (&v)[NV], unsigned long long u, const Reduce& R, int slot) {
   __shared__ double smd[NT / 32];
   __shared__ unsigned long long smu[NT / 32];
@@ -100,11 +113,11 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], unsigned long long 
   const unsigned nb = n_blocks(), bid = lin_bid();
 #pragma unroll
   for (int k = 0; k < NV; k++) {
-    double r = block_reduce<OP>(v[k], smd);
+    double r = block_reduce<OP, BAR, NTH>(v[k], smd);
     if (t == 0) R.partial_d[(size_t)k * R.max_blocks + bid] = r;
   }
   if (WITH_U) {
-    unsigned long long r = block_reduce_u(u, smu);
+    unsigned long long r = block_reduce_u<BAR, NTH>(u, smu);
     if (t == 0) R.partial_u[bid] = r;
   }
   if (t == 0) {
@@ -112,21 +125,21 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], unsigned long long 
     unsigned int tk = atomicAdd(R.ticket, 1u);
     is_last = (tk == nb - 1);
   }
-  __syncthreads();
+  red_sync<BAR, NTH>();
   if (!is_last) return;
   __threadfence();
+  const int nth = red_threads<BAR, NTH>();
 #pragma unroll
   for (int k = 0; k < NV; k++) {
     double a = OP::id();
-    for (unsigned i = t; i < nb; i += blockDim.x * blockDim.y * blockDim.z)
-      a = OP::f(a, __ldcg(&R.partial_d[(size_t)k * R.max_blocks + i]));
-    a = block_reduce<OP>(a, smd);
+    for (unsigned i = t; i < nb; i += nth) a = OP::f(a, __ldcg(&R.partial_d[(size_t)k * R.max_blocks + i]));
+    a = block_reduce<OP, BAR, NTH>(a, smd);
     if (t == 0) R.out_d[slot + k] = a;
   }
   if (WITH_U) {
     unsigned long long a = 0;
-    for (unsigned i = t; i < nb; i += blockDim.x * blockDim.y * blockDim.z) a += __ldcg(&R.partial_u[i]);
-    a = block_reduce_u(a, smu);
+    for (unsigned i = t; i < nb; i += nth) a += __ldcg(&R.partial_u[i]);
+    a = block_reduce_u<BAR, NTH>(a, smu);
     if (t == 0) R.out_u[slot] = a;
   }
   if (t == 0) *R.ticket = 0u;
@@ -728,9 +741,91 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 
 constexpr int BR_NN = BRICK_MAX_NODES;
-constexpr int BR_XS = 6 * BR_NN;   // doubles per vertex staging buffer: [x|w][3][BR_NN]
-constexpr int BR_EX = 24 * NTP;    // doubles per exchange buffer: [(p*3+r)][NTP]
-constexpr size_t BRICK_SMEM = (size_t)2 * (BR_XS + BR_EX) * sizeof(double) + 2 * BRICK_CTAB_BYTES + 2 * BRICK_GTAB_BYTES;
+constexpr int BR_XS = 6 * BR_NN;            // doubles per vertex staging buffer: [x|w][3][BR_NN]
+constexpr int BR_EX = BRICK_EX_ZERO + 4;    // doubles per exchange buffer (+ the zero slot, 16-byte multiple)
+constexpr int BR_NGT = 3;                   // gather-table buffers (the warp-specialised kernel stages two bricks ahead)
+constexpr size_t BRICK_SMEM = (size_t)2 * (BR_XS + BR_EX) * sizeof(double) + 2 * BRICK_CTAB_BYTES + BR_NGT * BRICK_GTAB_BYTES;
+
+// nodes of one brick <- exchange column (shared memory), thread j takes nodes j, j+128, ...
+__device__ __forceinline__ void brick_gather(const double* __restrict__ ex, const char* __restrict__ gt, const int tid,
+                                             const BrickDev& B, double* __restrict__ g, double* __restrict__ rout,
+                                             const long long stride) {
+  const int* T = reinterpret_cast<const int*>(gt);
+  const int nn = T[0], novf = T[1], nn4 = (nn + 3) & ~3;
+  const int* tnode = T + 4;
+  const int* tdst = tnode + nn4;
+  const uint4* tell = reinterpret_cast<const uint4*>(tdst + nn4);
+  for (int j = tid; j < nn; j += NTP) {
+    const uint4 q = tell[j];
+    const unsigned qq[4] = {q.x, q.y, q.z, q.w};
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {  // ascending (element id, local node) order; unused entries read the zero slot
+      const double* col = ex + ((qq[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+      s0 += col[0];
+      s1 += col[1];
+      s2 += col[2];
+    }
+    if (novf > 0) {  // node shared by more than 8 elements of the brick (irregular meshes)
+      const uint16_t* ov = reinterpret_cast<const uint16_t*>(tell + nn);
+      for (int i = 0; i < novf;) {
+        const int jj = ov[i], cnt = ov[i + 1];
+        if (jj == j)
+          for (int k = 0; k < cnt; k++) {
+            const double* col = ex + ov[i + 2 + k];
+            s0 += col[0];
+            s1 += col[1];
+            s2 += col[2];
+          }
+        i += 2 + cnt;
+      }
+    }
+    const int node = tnode[j], dst = tdst[j];
+    if (dst < 0) {
+      if (dst == -2) s0 = s1 = s2 = 0.0;  // fixed or not owned (Def.hpp:1226-1244)
+      g[node] = s0;
+      g[stride + node] = s1;
+      g[2 * stride + node] = s2;
+      if (rout) {
+        rout[node] = s0;
+        rout[stride + node] = s1;
+        rout[2 * stride + node] = s2;
+      }
+    } else {
+      B.partial[dst] = s0;
+      B.partial[B.npartial + dst] = s1;
+      B.partial[2 * B.npartial + dst] = s2;
+    }
+  }
+}
+
+// one hex of the brick: vertices through brick-local indices, contributions into the exchange column
+template <int STAGE>
+__device__ __forceinline__ void brick_element(const MeshDev& m, const double* __restrict__ xb, const char* __restrict__ cb,
+                                              double* __restrict__ exw, const int tid, double& val, unsigned long long& inv) {
+  const uint4 lc = *reinterpret_cast<const uint4*>(cb + tid * 16);
+  const int e_cur = reinterpret_cast<const int*>(cb + 2048)[tid];
+  const int off[8] = {(int)(lc.x & 0xffffu), (int)(lc.x >> 16), (int)(lc.y & 0xffffu), (int)(lc.y >> 16),
+                      (int)(lc.z & 0xffffu), (int)(lc.z >> 16), (int)(lc.w & 0xffffu), (int)(lc.w >> 16)};
+  double grad[8][3];
+  bool use = false;
+  if (e_cur >= 0) {
+    const IdxVerts<BR_NN> VC(xb, off), VO(xb + 3 * BR_NN, off);
+    bool valid;
+    const double mm = hex_metric_fast_v<STAGE, true>(VC, VO, valid, grad);
+    use = valid || STAGE == 0;  // Def.hpp:1219
+    bool counted = true;
+    if (m.elem_owned) counted = m.elem_owned[e_cur] != 0;
+    if (counted) {
+      val += mm;
+      inv += valid ? 0 : 1;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 8; p++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) exw[p * 3 + r] = use ? grad[p][r] : 0.0;
+}
 
 template <int STAGE>
 __global__ void __launch_bounds__(NTP, 2) k_brick_grad(const MeshDev m, const BrickDev B, const double* __restrict__ x,
@@ -742,11 +837,12 @@ __global__ void __launch_bounds__(NTP, 2) k_brick_grad(const MeshDev m, const Br
   double* const xs = sm;                    // [2][BR_XS]
   double* const exb = sm + 2 * BR_XS;       // [2][BR_EX]
   char* const ctb = reinterpret_cast<char*>(exb + 2 * BR_EX);  // [2][BRICK_CTAB_BYTES]
-  char* const gtb = ctb + 2 * BRICK_CTAB_BYTES;                // [2][BRICK_GTAB_BYTES]
+  char* const gtb = ctb + 2 * BRICK_CTAB_BYTES;                // [BR_NGT][BRICK_GTAB_BYTES] (two used here)
   const int tid = threadIdx.x;
   double val[1] = {0.0};
   unsigned long long inv = 0;
   const long long nbricks = B.nbricks, gstep = gridDim.x;
+  if (tid < 8) exb[(tid >> 2) * BR_EX + BRICK_EX_ZERO + (tid & 3)] = 0.0;
 
   // metadata registers: node ids this thread stages for the next brick, gather-table range of the current one
   int nid[3] = {0, 0, 0}, nn_s = 0, go0 = 0, go1 = 0;
@@ -787,61 +883,6 @@ __global__ void __launch_bounds__(NTP, 2) k_brick_grad(const MeshDev m, const Br
     for (int i = go0 + tid; i < go1; i += NTP) cp_async16(gb + (size_t)(i - go0) * 16, &B.gtab[i]);
     cp_async_commit();
   };
-  auto gather = [&](int pb) {
-    const double* ex = exb + (size_t)pb * BR_EX;  // ex[(p*3+r)*NTP + t]
-    const int* T = reinterpret_cast<const int*>(gtb + (size_t)pb * BRICK_GTAB_BYTES);
-    const int nn = T[0], novf = T[1], nn4 = (nn + 3) & ~3;
-    const int* tnode = T + 4;
-    const int* tdst = tnode + nn4;
-    const uint4* tell = reinterpret_cast<const uint4*>(tdst + nn4);
-    for (int j = tid; j < nn; j += NTP) {
-      const int node = tnode[j], dst = tdst[j];
-      const uint4 q = tell[j];
-      const unsigned qq[4] = {q.x, q.y, q.z, q.w};
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const unsigned ent = (qq[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-        const bool on = ent != 0xffffu;
-        const unsigned e2 = on ? ent : 0u;
-        const double* col = ex + (e2 & 7u) * 3 * NTP + (e2 >> 3);
-        const double v0 = col[0], v1 = col[NTP], v2 = col[2 * NTP];
-        s0 += on ? v0 : 0.0;
-        s1 += on ? v1 : 0.0;
-        s2 += on ? v2 : 0.0;
-      }
-      if (novf > 0) {  // node shared by more than 8 elements of the brick (irregular meshes)
-        const uint16_t* ov = reinterpret_cast<const uint16_t*>(tell + nn);
-        for (int i = 0; i < novf;) {
-          const int jj = ov[i], cnt = ov[i + 1];
-          if (jj == j)
-            for (int k = 0; k < cnt; k++) {
-              const unsigned ent = ov[i + 2 + k];
-              const double* col = ex + (ent & 7u) * 3 * NTP + (ent >> 3);
-              s0 += col[0];
-              s1 += col[NTP];
-              s2 += col[2 * NTP];
-            }
-          i += 2 + cnt;
-        }
-      }
-      if (dst < 0) {
-        if (dst == -2) s0 = s1 = s2 = 0.0;  // fixed or not owned (Def.hpp:1226-1244)
-        g[node] = s0;
-        g[stride + node] = s1;
-        g[2 * stride + node] = s2;
-        if (rout) {
-          rout[node] = s0;
-          rout[stride + node] = s1;
-          rout[2 * stride + node] = s2;
-        }
-      } else {
-        B.partial[dst] = s0;
-        B.partial[B.npartial + dst] = s1;
-        B.partial[2 * B.npartial + dst] = s2;
-      }
-    }
-  };
 
   long long brick = blockIdx.x;
   load_meta(brick, nbricks);
@@ -852,40 +893,136 @@ __global__ void __launch_bounds__(NTP, 2) k_brick_grad(const MeshDev m, const Br
     const int cur = it & 1;
     cp_async_wait_all();
     __syncthreads();  // staged vertices/tables of this brick and the exchange column of the previous one are complete
-    if (it > 0) gather(cur ^ 1);
+    if (it > 0) brick_gather(exb + (size_t)(cur ^ 1) * BR_EX, gtb + (size_t)(cur ^ 1) * BRICK_GTAB_BYTES, tid, B, g, rout, stride);
     issue(brick + gstep, cur ^ 1, cur);  // next brick's vertices; this brick's gather table (needed next iteration)
     load_meta(brick + 2 * gstep, brick + gstep);
-
-    const char* cb = ctb + (size_t)cur * BRICK_CTAB_BYTES;
-    const uint4 lc = *reinterpret_cast<const uint4*>(cb + tid * 16);
-    const int e_cur = reinterpret_cast<const int*>(cb + 2048)[tid];
-    const int off[8] = {(int)(lc.x & 0xffffu), (int)(lc.x >> 16), (int)(lc.y & 0xffffu), (int)(lc.y >> 16),
-                        (int)(lc.z & 0xffffu), (int)(lc.z >> 16), (int)(lc.w & 0xffffu), (int)(lc.w >> 16)};
-    double grad[8][3];
-    bool use = false;
-    if (e_cur >= 0) {
-      const double* xb = xs + (size_t)cur * BR_XS;
-      const IdxVerts<BR_NN> VC(xb, off), VO(xb + 3 * BR_NN, off);
-      bool valid;
-      const double mm = hex_metric_fast_v<STAGE, true>(VC, VO, valid, grad);
-      use = valid || STAGE == 0;  // Def.hpp:1219
-      bool counted = true;
-      if (m.elem_owned) counted = m.elem_owned[e_cur] != 0;
-      if (counted) {
-        val[0] += mm;
-        inv += valid ? 0 : 1;
-      }
-    }
-    double* exw = exb + (size_t)cur * BR_EX + tid;
-#pragma unroll
-    for (int p = 0; p < 8; p++)
-#pragma unroll
-      for (int r = 0; r < 3; r++) exw[(p * 3 + r) * NTP] = use ? grad[p][r] : 0.0;
+    brick_element<STAGE>(m, xs + (size_t)cur * BR_XS, ctb + (size_t)cur * BRICK_CTAB_BYTES,
+                         exb + (size_t)cur * BR_EX + tid * BRICK_EX_STRIDE, tid, val[0], inv);
   }
   cp_async_wait_all();
   __syncthreads();
-  if (it > 0) gather((it - 1) & 1);
+  if (it > 0) brick_gather(exb + (size_t)((it - 1) & 1) * BR_EX, gtb + (size_t)((it - 1) & 1) * BRICK_GTAB_BYTES, tid, B, g, rout, stride);
   grid_reduce<OpSum, 1, true>(val, inv, R, slot);
+}
+
+// Warp-specialised form of k_brick_grad (variant 5).  256 threads: warpgroup 0 (128 threads, 216 registers via
+// setmaxnreg) only evaluates elements; warpgroup 1 (40 registers) stages the next-but-one brick with cp.async and
+// gathers / stores the previous brick, so the FP64 pipe is not left idle during table walks, address arithmetic and
+// stores.  Hand-off through named barriers (ids 1-6); two vertex / exchange buffers, three gather-table buffers:
+//   STAGED[b&1]  helper -> compute   vertices + compute table of brick b are in shared memory
+//   READY[b&1]   compute -> helper   contributions of brick b written, its vertex buffer is free
+//   EXFREE[b&1]  helper -> compute   contributions of brick b-2 gathered, exchange buffer reusable
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+constexpr int WS_REG_COMPUTE = 216, WS_REG_HELPER = 40;  // (216 + 40) * 128 threads = half the register file
+
+template <int STAGE>
+__global__ void __launch_bounds__(2 * NTP, 2) k_brick_ws(const MeshDev m, const BrickDev B, const double* __restrict__ x,
+                                                         const double* __restrict__ w, const long long stride,
+                                                         double* __restrict__ g, double* __restrict__ rout, const Reduce R,
+                                                         const int slot) {
+  extern __shared__ double sm[];
+  double* const xs = sm;                    // [2][BR_XS]
+  double* const exb = sm + 2 * BR_XS;       // [2][BR_EX]
+  char* const ctb = reinterpret_cast<char*>(exb + 2 * BR_EX);  // [2][BRICK_CTAB_BYTES]
+  char* const gtb = ctb + 2 * BRICK_CTAB_BYTES;                // [BR_NGT][BRICK_GTAB_BYTES]
+  const int tid = threadIdx.x & (NTP - 1);
+  const long long nbricks = B.nbricks, gstep = gridDim.x, first = blockIdx.x;
+  const int n = first < nbricks ? (int)((nbricks - first + gstep - 1) / gstep) : 0;  // bricks of this CTA
+  enum { STAGED = 1, READY = 3, EXFREE = 5, COMPUTE = 8 };
+
+  if (threadIdx.x >= NTP) {
+    // ---------------------------------------------------------------- helper warpgroup
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_HELPER));
+    if (tid < 8) exb[(tid >> 2) * BR_EX + BRICK_EX_ZERO + (tid & 3)] = 0.0;
+    // metadata of the brick staged next, fetched one iteration early
+    int nn_s = 0, nid[3] = {0, 0, 0}, go0 = 0, go1 = 0;
+    auto load_meta = [&](int k) {
+      nn_s = 0;
+      go0 = go1 = 0;
+      if (k < n) {
+        const long long b = first + (long long)k * gstep;
+        nn_s = __ldg(&B.bnn[b]);
+        go0 = __ldg(&B.goff[b]);
+        go1 = __ldg(&B.goff[b + 1]);
+        const int* tn = reinterpret_cast<const int*>(B.gtab + go0) + 4;
+#pragma unroll
+        for (int q = 0; q < 3; q++) nid[q] = (tid + q * NTP < nn_s) ? __ldg(&tn[tid + q * NTP]) : 0;
+      }
+    };
+    auto stage = [&](int k, int gbuf) {  // vertices, compute table and gather table of this CTA's k-th brick
+      const long long b = first + (long long)k * gstep;
+      double* xb = xs + (size_t)(k & 1) * BR_XS;
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const int j = tid + q * NTP;
+        if (j < nn_s) {
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            cp_async8(xb + r * BR_NN + j, &x[r * stride + nid[q]]);
+            cp_async8(xb + (3 + r) * BR_NN + j, &w[r * stride + nid[q]]);
+          }
+        }
+      }
+      char* cb = ctb + (size_t)(k & 1) * BRICK_CTAB_BYTES;
+      const uint4* src = B.ctab + b * (BRICK_CTAB_BYTES / 16);
+      cp_async16(cb + tid * 16, src + tid);
+      if (tid < 32) cp_async16(cb + 2048 + tid * 16, src + 128 + tid);
+      char* gb = gtb + (size_t)gbuf * BRICK_GTAB_BYTES;
+      for (int i = go0 + tid; i < go1; i += NTP) cp_async16(gb + (size_t)(i - go0) * 16, &B.gtab[i]);
+      cp_async_commit();
+    };
+    load_meta(0);
+    for (int k = 0; k < 2 && k < n; k++) {
+      stage(k, k);
+      load_meta(k + 1);
+      cp_async_wait_all();
+      nbar_arrive(STAGED + (k & 1), 2 * NTP);
+    }
+    int gcur = 0;  // k % 3
+    for (int k = 0; k < n; k++) {
+      const int cur = k & 1;
+      nbar_sync(READY + cur, 2 * NTP);  // contributions of brick k written, its vertex buffer free; gather k-1 done
+      const bool more = k + 2 < n;
+      if (more) {
+        stage(k + 2, gcur == 0 ? 2 : gcur - 1);  // (k + 2) % 3
+        load_meta(k + 3);
+      }
+      brick_gather(exb + (size_t)cur * BR_EX, gtb + (size_t)gcur * BRICK_GTAB_BYTES, tid, B, g, rout, stride);
+      if (more) {
+        nbar_arrive(EXFREE + cur, 2 * NTP);
+        cp_async_wait_all();
+        nbar_arrive(STAGED + cur, 2 * NTP);
+      }
+      gcur = gcur == 2 ? 0 : gcur + 1;
+    }
+    return;
+  }
+  // ------------------------------------------------------------------ compute warpgroup
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REG_COMPUTE));
+  double val[1] = {0.0};
+  unsigned long long inv = 0;
+  for (int k = 0; k < n; k++) {
+    const int cur = k & 1;
+    nbar_sync(STAGED + cur, 2 * NTP);
+    // (the exchange column of brick k-2 must have been gathered before it is overwritten: the wait sits inside
+    //  brick_element's store phase in program order, i.e. after the FP64 work)
+    double cval = 0.0;
+    unsigned long long cinv = 0;
+    double stash[24];
+    brick_element<STAGE>(m, xs + (size_t)cur * BR_XS, ctb + (size_t)cur * BRICK_CTAB_BYTES, stash, tid, cval, cinv);
+    if (k >= 2) nbar_sync(EXFREE + cur, 2 * NTP);
+    double* exw = exb + (size_t)cur * BR_EX + tid * BRICK_EX_STRIDE;
+#pragma unroll
+    for (int q = 0; q < 24; q++) exw[q] = stash[q];
+    val[0] += cval;
+    inv += cinv;
+    nbar_arrive(READY + cur, 2 * NTP);
+  }
+  grid_reduce<OpSum, 1, true, COMPUTE, NTP>(val, inv, R, slot);
 }
 
 __global__ void __launch_bounds__(NT) k_brick_combine(const BrickDev B, const uint8_t* __restrict__ fixed,
@@ -913,30 +1050,26 @@ __global__ void __launch_bounds__(NT) k_brick_combine(const BrickDev B, const ui
   }
 }
 
+int g_grad_corners = 2;  // default-build gradient: 2 = pipelined element pass + gather, 1 = corner-parallel hex,
+                         // 0 = simple, 3 = quad-lane, 4 = bricks, 5 = warp-specialised bricks
 static bool launch_grad_bricks(cudaStream_t st, const MeshDev& m, const BrickDev& B, int stage, const double* x, const double* w,
                                long long stride, const uint8_t* fixed, const uint8_t* owned, double* g, double* rout,
                                const Reduce& R, int slot, double* em, int32_t* ef) {
-  if (STRICT || m.kind != KIND_HEX8) return false;
-  const size_t smem = BRICK_SMEM;
-  static int blocks_per_sm[2] = {0, 0};
-  auto k0 = k_brick_grad<0>;
-  auto k1 = k_brick_grad<1>;
-  if (!blocks_per_sm[stage]) {
-    if (stage == 0) {
-      cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[0], k0, NTP, smem);
-    } else {
-      cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[1], k1, NTP, smem);
-    }
-    if (blocks_per_sm[stage] < 1) blocks_per_sm[stage] = 1;
+  if (STRICT || m.kind != KIND_HEX8 || em || ef) return false;
+  const bool ws = g_grad_corners == 5;
+  void (*kern)(MeshDev, BrickDev, const double*, const double*, long long, double*, double*, Reduce, int) =
+      ws ? (stage == 0 ? k_brick_ws<0> : k_brick_ws<1>) : (stage == 0 ? k_brick_grad<0> : k_brick_grad<1>);
+  const int nthreads = ws ? 2 * NTP : NTP;
+  static int blocks_per_sm[2][2] = {{0, 0}, {0, 0}};
+  int& bps = blocks_per_sm[ws][stage];
+  if (!bps) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BRICK_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, nthreads, BRICK_SMEM);
+    if (bps < 1) bps = 1;
   }
-  const long long cap = 148LL * blocks_per_sm[stage];
+  const long long cap = 148LL * bps;
   const unsigned grid = (unsigned)(B.nbricks < cap ? (B.nbricks < 1 ? 1 : B.nbricks) : cap);
-  if (stage == 0)
-    k0<<<grid, NTP, smem, st>>>(m, B, x, w, stride, g, rout, R, slot);
-  else
-    k1<<<grid, NTP, smem, st>>>(m, B, x, w, stride, g, rout, R, slot);
+  kern<<<grid, nthreads, BRICK_SMEM, st>>>(m, B, x, w, stride, g, rout, R, slot);
   if (B.ncomb > 0) k_brick_combine<<<(unsigned)((B.ncomb + NT - 1) / NT), NT, 0, st>>>(B, fixed, owned, g, rout, stride);
   return true;
 }
@@ -1101,12 +1234,11 @@ __global__ void __launch_bounds__(NT) k_grad_elements(const MeshDev m, const dou
   grid_reduce<OpSum, 1, true>(val, inv, R, slot);
 }
 
-int g_grad_corners = 2;  // default-build gradient element pass: 2 = pipelined, 1 = corner-parallel hex, 0 = simple
 template <int FL>
 static void launch_grad_elements1(cudaStream_t st, const MeshDev& m, int stage, int use_ref, const double* x,
                                   const double* w, long long stride, double* eg, long long egs, const Reduce& R, int slot,
                                   double* em, int32_t* ef) {
-  if (!STRICT && g_grad_corners == 2) {
+  if (!STRICT && (g_grad_corners == 2 || g_grad_corners >= 4)) {
     if (stage == 0)
       launch_elem_pipe<FL, 0, true, true, false>(st, m, x, nullptr, w, stride, 0.0, eg, egs, R, slot, em, ef);
     else if (use_ref)

@@ -48,8 +48,9 @@ struct BrickDev {
   // gather table, one 16-byte-aligned blob per brick:
   //   int32 nn, novf, 0, 0 | int32 node[nn4] | int32 dst[nn4] | uint16 ell[nn][8] | uint16 ovf[pad8(novf)]
   //   node: global ids ascending.  dst: -1 all adjacent elements inside the brick, free node -> cg_g; -2 same but
-  //   fixed / not owned -> 0; >= 0 index of this brick's partial sum.  ell: the node's first 8 contributions t*8+p in
-  //   ascending (element id, local node) order, 0xFFFF = none; ovf: [j, count, entries...] for the 9th onward.
+  //   fixed / not owned -> 0; >= 0 index of this brick's partial sum.  ell: the node's first 8 contributions (exchange
+  //   column offsets, see BRICK_EX_STRIDE) in ascending (element id, local node) order; ovf: [j, count, entries...]
+  //   for the 9th onward.
   const int32_t* goff;       // [nbricks+1] blob offsets in 16-byte units
   const uint4* gtab;
   double* partial;           // [3][npartial] brick-surface partial sums
@@ -60,9 +61,13 @@ struct BrickDev {
   const int32_t* comb_ent;   // partial indices, ascending brick id
 };
 constexpr int BRICK_ELEMS = 128;      // = NTP of the pipelined kernels
-constexpr int BRICK_MAX_NODES = 384;  // a brick is cut short when its distinct nodes would exceed this
+constexpr int BRICK_MAX_NODES = 320;  // a brick is cut short when its distinct nodes would exceed this
 constexpr int BRICK_CTAB_BYTES = 2560;
 constexpr int BRICK_GTAB_BYTES = 16 + 8 * BRICK_MAX_NODES + 16 * BRICK_MAX_NODES;  // overflow shares the slack
+// exchange column: contribution (p, r) of slot t at t*BRICK_EX_STRIDE + p*3 + r (odd stride: conflict-free writes);
+// an ELL entry is t*BRICK_EX_STRIDE + p*3; unused ELL entries point at three zeros behind the last column.
+constexpr int BRICK_EX_STRIDE = 25;
+constexpr int BRICK_EX_ZERO = BRICK_ELEMS * BRICK_EX_STRIDE;
 
 struct Launchers {
   // metric of (x + alpha*s on unfixed nodes) vs reference w; result: out_d[slot] = sum, out_u[slot] = #invalid.

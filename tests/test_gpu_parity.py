@@ -277,14 +277,15 @@ def test_errors_are_reported_not_swallowed():
 
 
 @pytest.mark.parametrize("kind", ["sgrid", "hex8"])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_kernel_variants_agree_with_oracle(kind, variant):
-    """All default-build hex kernel variants (0 simple, 1 corner-parallel, 2 pipelined, 3 quad-lane) against the oracle."""
+    """All default-build hex kernel variants (0 simple, 1 corner-parallel, 2 pipelined, 3 quad-lane, 4 bricks,
+    5 warp-specialised bricks) against the oracle."""
     for stage, eps in ((1, 0.25), (0, 1.0), (1, 1.0)):
         g, o = pair(kind, 11, eps, strict=0)
-        g.set_option("variant_metric_corners", min(variant, 3) if variant != 4 else 2)
-        g.set_option("variant_grad_corners", variant)  # 4 = scratch-free brick gradient (hex8), needs keep_element_metrics off
-        if variant == 4:
+        g.set_option("variant_metric_corners", variant if variant < 4 else 2)
+        g.set_option("variant_grad_corners", variant)  # 4/5 = scratch-free brick gradient (hex8), needs keep_element_metrics off
+        if variant >= 4:
             g.set_option("keep_element_metrics", 0)
         n = g.num_nodes_local
         s = meshes.seeded_field(n, 5, 0.01 / 11)
@@ -294,7 +295,7 @@ def test_kernel_variants_agree_with_oracle(kind, variant):
             mg, ng = g.total_metric(stage, alpha)
             mo, no = o.total_metric(stage, alpha)
             assert ng == no and abs(mg - mo) <= 1e-12 * abs(mo)
-            if variant != 4:
+            if variant < 4:
                 assert rel(g.element_metrics()[0], o.element_metrics()[0]) < 1e-12
         mg, ng = g.metric_and_gradient(stage)
         mo, no = o.metric_and_gradient(stage)
@@ -357,6 +358,65 @@ def test_anisotropic_odd_sized_mesh(kind, variant):
     sg, so = g.run_algorithm(5, 0.0), o.run_algorithm(5, 0.0)
     assert rel(g.download("coordinates"), o.download("coordinates")) < 1e-9
     g.set_option("variant_metric_corners", 2)
+    g.set_option("variant_grad_corners", 2)
+
+
+def _fan_mesh(nz):
+    """5 quads around an irregular centre vertex, extruded nz layers: centre-axis nodes belong to 10 hexes."""
+    ang = 2 * np.pi * np.arange(5) / 5
+    pts2 = [(0.0, 0.0)] + [(np.cos(a), np.sin(a)) for a in ang] + [(1.3 * np.cos(a + np.pi / 5), 1.3 * np.sin(a + np.pi / 5)) for a in ang]
+    quads = [(0, 1 + i, 6 + i, 1 + (i + 1) % 5) for i in range(5)]  # counter-clockwise
+    n2 = len(pts2)
+    W = np.array([[x, y, k * 0.5] for k in range(nz + 1) for (x, y) in pts2]).T.copy()
+    conn = np.array([[q[0] + k * n2, q[1] + k * n2, q[2] + k * n2, q[3] + k * n2,
+                      q[0] + (k + 1) * n2, q[1] + (k + 1) * n2, q[2] + (k + 1) * n2, q[3] + (k + 1) * n2]
+                     for k in range(nz) for q in quads], dtype=np.int32)
+    fixed = np.ones(W.shape[1], dtype=np.uint8)
+    for k in range(1, nz):
+        fixed[k * n2] = 0  # free: interior centre-axis nodes (valence 10)
+    return np.ascontiguousarray(W), np.ascontiguousarray(conn), fixed
+
+
+def _isolated_hexes(n):
+    """n disjoint unit cubes (no shared nodes): 128 elements touch 1024 nodes, so bricks must be cut short."""
+    corner = np.array([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)], dtype=np.float64)
+    W = np.concatenate([corner + np.array([2.0 * (e % 7), 2.0 * ((e // 7) % 7), 2.0 * (e // 49)]) for e in range(n)]).T.copy()
+    conn = np.arange(8 * n, dtype=np.int32).reshape(n, 8)
+    return np.ascontiguousarray(W), conn, np.zeros(8 * n, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("mesh", ["fan", "isolated"])
+@pytest.mark.parametrize("variant", [2, 4, 5])
+def test_brick_gradient_on_irregular_meshes(mesh, variant):
+    """Brick gradient tables on meshes a lattice never produces: nodes shared by more than 8 elements of one brick
+    (ELL overflow list), bricks cut short by the distinct-node cap, partial sums across the cut."""
+    W, conn, fixed = _fan_mesh(40) if mesh == "fan" else _isolated_hexes(300)
+    rng = np.random.default_rng(11)
+    X = np.ascontiguousarray(W + 0.08 * (rng.random(W.shape) - 0.5) * (fixed == 0)[None, :])
+
+    def mk(api, opts):
+        c = api.create()
+        for kk, v in opts.items():
+            c.set_option(kk, v)
+        c.set_unstructured(8, W.shape[1], conn)
+        c.set_fixed_mask(fixed)
+        c.commit()
+        for f, v in (("coordinates", X), ("coordinates_N", X), ("coordinates_NM1", W)):
+            c.upload(f, v)
+        return c
+    g = mk(pb.api, {"variant_grad_corners": variant, "cache_metric": 0, "keep_element_metrics": 0})
+    o = mk(oracle, {"real_is_double": 1})
+    for stage in (0, 1):
+        mg, ng = g.metric_and_gradient(stage)
+        mo, no = o.metric_and_gradient(stage)
+        assert ng == no and abs(mg - mo) <= 1e-12 * max(abs(mo), 1e-300)
+        go = o.download("cg_g")
+        if np.max(np.abs(go)) > 0:
+            assert rel(g.download("cg_g"), go) < 1e-12
+        assert np.array_equal(g.download("cg_r"), g.download("cg_g"))
+        a = g.download("cg_g").copy()
+        g.metric_and_gradient(stage)
+        assert np.array_equal(a, g.download("cg_g"))
     g.set_option("variant_grad_corners", 2)
 
 
