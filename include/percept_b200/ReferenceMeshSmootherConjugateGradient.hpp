@@ -16,8 +16,13 @@
 #define PERCEPT_B200_REFERENCE_MESH_SMOOTHER_CG_HPP
 
 #include <array>
+#include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <fstream>
 #include <functional>
+#include <iomanip>
+#include <limits>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -49,7 +54,59 @@ struct StructuredBlock {  // structured/StructuredBlock.hpp:31-101 (sizes + boun
   };
   std::vector<BC> m_boundaryConditions;
   std::vector<ZoneConnectivity> m_zoneConnectivity;
+  // host copy of the block coordinates (the reference's m_sgrid_coords), SoA planes x|y|z, i fastest; may be empty
+  std::vector<double> m_sgrid_coords;
   size_t num_nodes() const { return (size_t)node_size[0] * node_size[1] * node_size[2]; }
+  // StructuredBlock::dump_vtk (structured/StructuredBlock.cpp:297-445): one ASCII .vts piece, 4 decimals
+  void dump_vtk(const std::string& file_prefix, unsigned iblock, size_t nblocks) const {
+    std::ofstream out((file_prefix + "." + std::to_string(iblock) + ".vts").c_str());
+    char buf[1024];
+    std::snprintf(buf, sizeof buf,
+                  "<VTKFile type=\"StructuredGrid\" version=\"1.0\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n"
+                  "  <StructuredGrid WholeExtent=\"0 %u 0 %u 0 %u\">\n"
+                  "  <Piece Extent=\"0 %u 0 %u 0 %u\">\n"
+                  "    <PointData>\n"
+                  "    </PointData>\n",
+                  node_size[0] - 1, node_size[1] - 1, node_size[2] - 1, node_size[0] - 1, node_size[1] - 1, node_size[2] - 1);
+    out << buf << std::endl;
+    out << "    <Points>\n"
+           "       <DataArray type=\"Float64\" Name=\"Points\"  NumberOfComponents=\"3\" format=\"ascii\">\n";
+    out.precision(4);
+    out << std::fixed;
+    const size_t n = num_nodes();
+    for (size_t p = 0; p < n && m_sgrid_coords.size() == 3 * n; p++) {
+      out << "         ";
+      for (unsigned ic = 0; ic < 3; ic++) {
+        double val = m_sgrid_coords[ic * n + p];
+        if (std::fabs(val) < std::numeric_limits<double>::epsilon()) val = 0.0;
+        out << std::setw(16) << val;
+      }
+      out << "\n";
+    }
+    out << "       </DataArray>\n"
+           "    </Points>\n";
+    out.unsetf(std::ios_base::floatfield);
+    out.precision(6);
+    const size_t ncell = (size_t)(node_size[0] - 1) * (node_size[1] - 1) * (node_size[2] - 1);
+    out << "    <CellData Scalars=\" proc_id  block_id\">\n"
+           "       <DataArray Name=\"proc_id\" type=\"Int32\" format=\"ascii\">\n         ";
+    for (size_t e = 1; e <= ncell; e++) {
+      out << " " << 0;
+      if (e % 10 == 0) out << "\n         ";
+    }
+    out << "\n       </DataArray>\n"
+           "       <DataArray Name=\"block_id\" type=\"Float32\" format=\"ascii\">\n         ";
+    for (size_t e = 1; e <= ncell; e++) {
+      out << " " << double(iblock) / double(nblocks);
+      if (e % 10 == 0) out << "\n         ";
+    }
+    out << "\n       </DataArray>\n"
+           "    </CellData>\n"
+           "  </Piece>\n"
+           "  </StructuredGrid>\n"
+           "</VTKFile>\n"
+        << std::endl;
+  }
 };
 
 class PerceptMesh;
@@ -67,14 +124,22 @@ class BlockStructuredGrid {  // structured/BlockStructuredGrid.hpp:25-154
     const int n0 = (int)sizes[0], n1 = (int)sizes[1], n2 = (int)sizes[2];
     b->m_boundaryConditions = {{{{1, 1, 1}}, {{1, n1, n2}}},   {{{n0, 1, 1}}, {{n0, n1, n2}}}, {{{1, 1, 1}}, {{n0, 1, n2}}},
                                {{{1, n1, 1}}, {{n0, n1, n2}}}, {{{1, 1, 1}}, {{n0, n1, 1}}},   {{{1, 1, n2}}, {{n0, n1, n2}}}};
+    b->m_sgrid_coords.resize(3 * b->num_nodes());
+    pms_fixture_cube(sizes[0], sizes[1], sizes[2], widths.data(), offsets.data(), b->m_sgrid_coords.data());
     bsg->m_sblocks.push_back(b);
-    bsg->m_fixture_widths = widths;
-    bsg->m_fixture_offsets = offsets;
-    bsg->m_is_fixture = true;
     return bsg;
   }
-  bool m_is_fixture = false;
-  std::array<double, 3> m_fixture_widths{{1, 1, 1}}, m_fixture_offsets{{0, 0, 0}};
+  // BlockStructuredGrid::dump_vtk / create_pvd (structured/BlockStructuredGrid.cpp:62-99, 185-200): .pvd + one .vts per block
+  void dump_vtk(const std::string& file_prefix) const {
+    std::ofstream out((file_prefix + ".pvd").c_str());
+    out << "<VTKFile type=\"Collection\" version=\"1.0\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n"
+        << "  <Collection>\n";
+    for (unsigned ib = 0; ib < m_sblocks.size(); ib++) {
+      out << "      <DataSet part=\"" << ib << "\" file=\"" << file_prefix << "." << ib << ".vts\"/>" << std::endl;
+      m_sblocks[ib]->dump_vtk(file_prefix, ib, m_sblocks.size());
+    }
+    out << "  </Collection>\n</VTKFile>\n";
+  }
 };
 
 struct SGridSelector {  // MeshType.hpp:149-153
@@ -159,13 +224,11 @@ class PerceptMesh {
   void add_coordinate_state_fields() {
     if (!m_committed) check(m_ctx, pms_commit(m_ctx));
     m_committed = true;
-    if (m_bsg && m_bsg->m_is_fixture) {  // fixture_1 fills "coordinates"
-      auto& b = *m_bsg->m_sblocks[0];
-      std::vector<double> x(3 * b.num_nodes());
-      pms_fixture_cube(b.node_size[0], b.node_size[1], b.node_size[2], m_bsg->m_fixture_widths.data(),
-                       m_bsg->m_fixture_offsets.data(), x.data());
-      set_field("coordinates", x.data(), PMS_SOA, 0);
-    }
+    if (m_bsg)  // the grid's own coordinates (fixture_1, a refiner's output, a reader) become the "coordinates" field
+      for (size_t ib = 0; ib < m_bsg->m_sblocks.size(); ib++) {
+        auto& b = *m_bsg->m_sblocks[ib];
+        if (b.m_sgrid_coords.size() == 3 * b.num_nodes()) set_field("coordinates", b.m_sgrid_coords.data(), PMS_SOA, (int)ib);
+      }
   }
   bool committed() const { return m_committed; }
   void set_fixed_mask(const uint8_t* mask) { check(m_ctx, pms_set_fixed_mask(m_ctx, mask)); }
@@ -231,6 +294,66 @@ struct SGridBoundarySelector : public SGridSelector {
 };
 
 enum { MS_VERTEX, MS_CURVE, MS_SURFACE, MS_VOLUME, MS_ON_BOUNDARY, MS_NOT_ON_BOUNDARY };  // MeshType.hpp:29-38
+
+// ---- StructuredGridRefiner (structured/StructuredGridRefiner.hpp:19-52, .cpp:40-170) -----------------------------
+// 2x refinement of every block: do_refine() fills m_output (sizes 2n-1, boundary conditions and zone connectivity with
+// the 1-based ranges mapped r -> 2r-1, refined coordinates).  The coordinates are prolonged on the GPU
+// (pms_refine_structured_field); m_output carries a host copy like any other BlockStructuredGrid of this facade.
+class StructuredGridRefiner {
+ public:
+  std::shared_ptr<BlockStructuredGrid> m_input, m_output;
+  int m_debug;
+  explicit StructuredGridRefiner(std::shared_ptr<BlockStructuredGrid> input, int debug = 0, int device = 0)
+      : m_input(input), m_output(new BlockStructuredGrid()), m_debug(debug), m_device(device) {}
+
+  unsigned do_refine() {
+    struct Guard {  // two short-lived contexts: the coarse grid and its refinement
+      pms_ctx* c = nullptr;
+      ~Guard() {
+        if (c) pms_destroy(c);
+      }
+    } ci, co;
+    if (pms_create(&ci.c, m_device) != PMS_OK || pms_create(&co.c, m_device) != PMS_OK)
+      throw std::runtime_error("percept_b200: StructuredGridRefiner: cannot create a device context");
+    for (auto& b : m_input->m_sblocks) {
+      int id = -1;
+      check(ci.c, pms_add_structured_block(ci.c, b->node_size.data(), &id));
+      for (auto& bc : b->m_boundaryConditions) check(ci.c, pms_block_add_boundary_condition(ci.c, id, bc.beg.data(), bc.end.data()));
+    }
+    for (size_t ib = 0; ib < m_input->m_sblocks.size(); ib++)
+      for (auto& z : m_input->m_sblocks[ib]->m_zoneConnectivity)
+        check(ci.c, pms_block_add_zone_connectivity(ci.c, (int)ib, z.donor, z.transform.data(), z.owner_beg.data(),
+                                                    z.owner_end.data(), z.donor_beg.data(), z.donor_end.data()));
+    check(ci.c, pms_commit(ci.c));
+    for (size_t ib = 0; ib < m_input->m_sblocks.size(); ib++) {
+      auto& b = *m_input->m_sblocks[ib];
+      if (b.m_sgrid_coords.size() != 3 * b.num_nodes()) throw std::runtime_error("percept_b200: StructuredGridRefiner: input block has no coordinates");
+      check(ci.c, pms_field_upload(ci.c, "coordinates", (int)ib, b.m_sgrid_coords.data(), PMS_SOA));
+    }
+    unsigned long long num_refined_cells = 0;
+    check(co.c, pms_refine_structured_topology(ci.c, co.c, &num_refined_cells));
+    check(co.c, pms_commit(co.c));
+    check(co.c, pms_refine_structured_field(ci.c, "coordinates", co.c, "coordinates"));
+    // the refined grid description (StructuredGridRefiner.cpp:55-154), m_index_base = 1
+    m_output->m_sblocks.resize(0);
+    auto map3 = [](const std::array<int, 3>& r) { return std::array<int, 3>{{2 * r[0] - 1, 2 * r[1] - 1, 2 * r[2] - 1}}; };
+    for (size_t ib = 0; ib < m_input->m_sblocks.size(); ib++) {
+      auto& b = *m_input->m_sblocks[ib];
+      auto nb = std::make_shared<StructuredBlock>();
+      for (int d = 0; d < 3; d++) nb->node_size[d] = 2 * b.node_size[d] - 1;
+      for (auto& bc : b.m_boundaryConditions) nb->m_boundaryConditions.push_back({map3(bc.beg), map3(bc.end)});
+      for (auto& z : b.m_zoneConnectivity)
+        nb->m_zoneConnectivity.push_back({z.donor, z.transform, map3(z.owner_beg), map3(z.owner_end), map3(z.donor_beg), map3(z.donor_end)});
+      nb->m_sgrid_coords.resize(3 * nb->num_nodes());
+      check(co.c, pms_field_download(co.c, "coordinates", (int)ib, nb->m_sgrid_coords.data(), PMS_SOA));
+      m_output->m_sblocks.push_back(nb);
+    }
+    return (unsigned)num_refined_cells;
+  }
+
+ private:
+  int m_device;
+};
 
 // ---- smoother class hierarchy ------------------------------------------------------------------------------------
 template <typename MeshType>

@@ -199,13 +199,26 @@ int pms_set_interface(pms_ctx* ctx, int n_neighbors, const int* neighbor_ranks, 
 int pms_halo_exchange(pms_ctx* ctx, const char* name);
 
 /* ---- instrumentation --------------------------------------------------------- */
+/* ---- structured 2x refinement feeding the smoother -------------------------------------------------
+ * Replaces StructuredGridRefiner::do_refine (structured/StructuredGridRefiner.cpp:40-170, .hpp:19-52) and
+ * StructuredGridRefinerImpl::refine (structured/StructuredGridRefinerDef.hpp:43-226).
+ * 1. pms_refine_structured_topology(coarse, fine, &ncells): `fine` is a fresh ctx (no mesh); it receives one block
+ *    of 2n-1 nodes per direction for every block of `coarse`, with the 1-based boundary-condition and
+ *    zone-connectivity ranges mapped r -> 2r-1.  Returns the refined cell count like do_refine().  Host only.
+ * 2. caller commits `fine` (pms_commit) and chooses fixed nodes (e.g. pms_select_boundary_sgrid).
+ * 3. pms_refine_structured_field(coarse, "coordinates", fine, "coordinates"): device prolongation of a 3-component
+ *    nodal field: vertices copied, edge midpoints 0.5*(a+b), face centres and cell centroids summed in the
+ *    reference's order (bit-identical to it).  Both ctx on the same GPU; stream-ordered, no host sync.          */
+int pms_refine_structured_topology(const pms_ctx* coarse, pms_ctx* fine, unsigned long long* num_refined_cells);
+int pms_refine_structured_field(pms_ctx* coarse, const char* src_field, pms_ctx* fine, const char* dst_field);
+
 /* kernels launched by this ctx since creation (bench.py's gpu_launches).        */
 int pms_launch_count(const pms_ctx* ctx, uint64_t* n);
 /* CUDA stream of the ctx as an opaque handle, for event timing on that stream. */
 int pms_stream(const pms_ctx* ctx, void** stream);
 int pms_synchronize(pms_ctx* ctx);
 /* accumulated device time (ms, CUDA events on the ctx stream) per kernel family:
- * names = "metric","gradient","blas1","update","alpha0","edge","halo".          */
+ * names = "metric","gradient","blas1","update","alpha0","edge","halo","refine".          */
 int pms_kernel_time_ms(pms_ctx* ctx, const char* family, double* ms, uint64_t* launches);
 int pms_kernel_time_reset(pms_ctx* ctx);
 int pms_set_timing(pms_ctx* ctx, int enabled);

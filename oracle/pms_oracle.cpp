@@ -1559,6 +1559,105 @@ int orc_get_element_metrics(orc_ctx* c, double* metric, int32_t* flag) {
   if (flag) memcpy(flag, c->elem_flag.data(), c->nelems * sizeof(int32_t));
   return 0;
 }
+// ---- StructuredGridRefiner ----------------------------------------------------------------------
+// Host part of do_refine_structured (structured/StructuredGridRefiner.cpp:40-170): every block gets 2n-1 nodes per
+// direction (get_new_sizes, :19-38); the 1-based boundary-condition and zone-connectivity ranges map r -> 2(r-1)+1
+// (class member m_index_base = 1, StructuredGridRefiner.hpp:26; :107-154).
+int orc_refine_structured_topology(const orc_ctx* coarse, orc_ctx* fine, unsigned long long* num_refined_cells) {
+  orc_ctx* c = fine;
+  ORC_TRY
+  if (!coarse->structured) throw OrcError(2, "refiner input is not a structured grid");
+  if (fine->committed || fine->structured || fine->topo != 0) throw OrcError(2, "refiner output ctx must be empty");
+  const int base = 1;
+  unsigned long long ncell = 0;
+  for (const Block& b : coarse->blocks) {
+    Block nb;
+    for (int d = 0; d < 3; d++) nb.n[d] = 2 * b.n[d] - 1;
+    nb.off = 0;
+    for (const BC& bc : b.bcs) {
+      BC r = bc;
+      for (int d = 0; d < 3; d++) {
+        r.beg[d] = 2 * (bc.beg[d] - base) + base;
+        r.end[d] = 2 * (bc.end[d] - base) + base;
+      }
+      nb.bcs.push_back(r);
+    }
+    for (const Zone& z : b.zones) {
+      Zone r = z;
+      for (int d = 0; d < 3; d++) {
+        r.owner_beg[d] = 2 * (z.owner_beg[d] - base) + base;
+        r.owner_end[d] = 2 * (z.owner_end[d] - base) + base;
+        r.donor_beg[d] = 2 * (z.donor_beg[d] - base) + base;
+        r.donor_end[d] = 2 * (z.donor_end[d] - base) + base;
+      }
+      nb.zones.push_back(r);
+    }
+    ncell += (unsigned long long)nb.ncells();
+    fine->blocks.push_back(nb);
+  }
+  fine->structured = true;
+  if (num_refined_cells) *num_refined_cells = ncell;
+  ORC_CATCH
+}
+
+// StructuredGridRefinerImpl::operator() (structured/StructuredGridRefinerDef.hpp:134-222), one call per INPUT node:
+// vertex copy, the 3 edge midpoints, the 3 face centres and the cell centroid it owns, sums in the reference's order.
+int orc_refine_structured_field(orc_ctx* coarse, const char* src_field, orc_ctx* fine, const char* dst_field) {
+  orc_ctx* c = fine;
+  ORC_TRY
+  if (!coarse->committed || !fine->committed) throw OrcError(2, "refiner needs committed grids");
+  if (coarse->blocks.size() != fine->blocks.size()) throw OrcError(2, "grids do not match");
+  const Field& fi = coarse->fields.at(src_field);
+  Field& fo = fine->fields.at(dst_field);
+  if (fi.ncomp != 3 || fo.ncomp != 3) throw OrcError(2, "refiner prolongs 3-component nodal fields");
+  const size_t Ni = coarse->N, No = fine->N;
+  for (size_t ib = 0; ib < coarse->blocks.size(); ib++) {
+    const Block& bi = coarse->blocks[ib];
+    const Block& bo = fine->blocks[ib];
+    for (int d = 0; d < 3; d++)
+      if (bo.n[d] != 2 * bi.n[d] - 1) throw OrcError(2, "output block is not the 2x refinement of the input block");
+    auto in = [&](unsigned i, unsigned j, unsigned k, unsigned ic) { return fi.d[ic * Ni + bi.node(i, j, k)]; };
+    auto out = [&](unsigned i, unsigned j, unsigned k, unsigned ic) -> double& { return fo.d[ic * No + bo.node(i, j, k)]; };
+    const unsigned node_max[3] = {bi.n[0] - 1, bi.n[1] - 1, bi.n[2] - 1};
+    for (unsigned k = 0; k < bi.n[2]; k++)
+      for (unsigned j = 0; j < bi.n[1]; j++)
+        for (unsigned i = 0; i < bi.n[0]; i++) {
+          const unsigned indx[3] = {i, j, k};
+          const unsigned oindx[3] = {2 * i, 2 * j, 2 * k};
+          for (unsigned ic = 0; ic < 3; ic++) out(oindx[0], oindx[1], oindx[2], ic) = in(i, j, k, ic);  // vertices
+          const unsigned delta[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+          for (unsigned ll = 0; ll < 3; ll++)  // edges
+            if (indx[ll] < node_max[ll])
+              for (unsigned ic = 0; ic < 3; ic++)
+                out(oindx[0] + delta[ll][0], oindx[1] + delta[ll][1], oindx[2] + delta[ll][2], ic) =
+                    0.5 * (in(i, j, k, ic) + in(i + delta[ll][0], j + delta[ll][1], k + delta[ll][2], ic));
+          for (unsigned ll = 0; ll < 3; ll++) {  // faces
+            const unsigned addo[3][3] = {{0, 1, 1}, {1, 0, 1}, {1, 1, 0}};
+            const unsigned lc[3] = {ll, (ll + 1) % 3, (ll + 2) % 3};
+            if (indx[lc[1]] < node_max[lc[1]] && indx[lc[2]] < node_max[lc[2]])
+              for (unsigned ic = 0; ic < 3; ic++) {
+                double& o = out(oindx[0] + addo[ll][0], oindx[1] + addo[ll][1], oindx[2] + addo[ll][2], ic);
+                o = 0;
+                for (unsigned ii = 0; ii < 2; ii++)
+                  for (unsigned jj = 0; jj < 2; jj++) {
+                    const unsigned add[3][3] = {{0, ii, jj}, {ii, 0, jj}, {ii, jj, 0}};
+                    o += 0.25 * in(i + add[ll][0], j + add[ll][1], k + add[ll][2], ic);
+                  }
+              }
+          }
+          if (i < node_max[0] && j < node_max[1] && k < node_max[2])  // centroid
+            for (unsigned ic = 0; ic < 3; ic++) {
+              double& o = out(oindx[0] + 1, oindx[1] + 1, oindx[2] + 1, ic);
+              o = 0;
+              for (unsigned a = 0; a < 2; a++)
+                for (unsigned b = 0; b < 2; b++)
+                  for (unsigned cc = 0; cc < 2; cc++) o += 0.125 * in(i + a, j + b, k + cc, ic);
+            }
+        }
+  }
+  ORC_CATCH
+}
+
 int orc_state_init(orc_ctx* c, orc_state* st) {
   memset(st, 0, sizeof(*st));
   st->d0 = 1;

@@ -80,6 +80,8 @@ class Api:
         "state_init": [C.POINTER(State)],
         "run_one_iteration": [C.POINTER(State), C.c_double, _dp],
         "run_algorithm": [C.c_int, C.c_double, C.c_char_p, C.POINTER(State)],
+        "refine_structured_topology": [C.c_void_p, C.POINTER(C.c_ulonglong)],
+        "refine_structured_field": [C.c_char_p, C.c_void_p, C.c_char_p],
     }
     # product-only entry points (absent from the oracle twin)
     _SIGS_PRODUCT = {
@@ -197,6 +199,22 @@ class Ctx:
 
     def commit(self):
         self._call("commit")
+
+    # ---- StructuredGridRefiner (structured/StructuredGridRefiner.cpp:40-170) ----
+    def refine_topology(self, fine):
+        """Fill the empty ctx `fine` with the 2x refinement of this grid's blocks; returns the refined cell count."""
+        n = C.c_ulonglong(0)
+        rc = self.api.fn["refine_structured_topology"](self.p, fine.p, C.byref(n))
+        if rc != 0:
+            raise SmootherError(rc, self.api._last_error(fine.p).decode())
+        fine.block_sizes = [tuple(2 * v - 1 for v in b) for b in self.block_sizes]
+        return int(n.value)
+
+    def refine_field(self, src_field, fine, dst_field):
+        """2x prolongation of a 3-component nodal field onto the committed refined grid `fine`."""
+        rc = self.api.fn["refine_structured_field"](self.p, src_field.encode(), fine.p, dst_field.encode())
+        if rc != 0:
+            raise SmootherError(rc, self.api._last_error(fine.p).decode())
 
     @property
     def num_nodes_local(self):

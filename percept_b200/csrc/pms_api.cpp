@@ -1498,6 +1498,88 @@ int pms_copy_field(pms_ctx* c, const char* dst, const char* src) {
   PMS_CATCH
 }
 
+// StructuredGridRefiner::do_refine_structured, host part (structured/StructuredGridRefiner.cpp:40-170): sizes 2n-1
+// (get_new_sizes :19-38), 1-based BC / zone-connectivity ranges r -> 2(r-1)+1 (m_index_base = 1, .hpp:26).
+int pms_refine_structured_topology(const pms_ctx* coarse, pms_ctx* c, unsigned long long* num_refined_cells) {
+  PMS_TRY
+  if (!coarse || !coarse->structured) throw PmsError(PMS_ERR_ARG, "refiner input is not a structured grid");
+  if (c == coarse || c->committed || c->structured || c->topo != 0) throw PmsError(PMS_ERR_ARG, "refiner output ctx must be empty");
+  const int base = 1;
+  unsigned long long ncell = 0;
+  for (const HBlock& b : coarse->blocks) {
+    HBlock nb;
+    for (int d = 0; d < 3; d++) {
+      if (2ull * b.n[d] - 1 > 0x7fffffffull) throw PmsError(PMS_ERR_ARG, "refined block too large");
+      nb.n[d] = 2 * b.n[d] - 1;
+    }
+    for (const HBC& bc : b.bcs) {
+      HBC r = bc;
+      for (int d = 0; d < 3; d++) {
+        r.beg[d] = 2 * (bc.beg[d] - base) + base;
+        r.end[d] = 2 * (bc.end[d] - base) + base;
+      }
+      nb.bcs.push_back(r);
+    }
+    for (const HZone& z : b.zones) {
+      HZone r = z;
+      for (int d = 0; d < 3; d++) {
+        r.owner_beg[d] = 2 * (z.owner_beg[d] - base) + base;
+        r.owner_end[d] = 2 * (z.owner_end[d] - base) + base;
+        r.donor_beg[d] = 2 * (z.donor_beg[d] - base) + base;
+        r.donor_end[d] = 2 * (z.donor_end[d] - base) + base;
+      }
+      nb.zones.push_back(r);
+    }
+    ncell += (unsigned long long)nb.ncells();
+    c->blocks.push_back(nb);
+  }
+  c->structured = true;
+  if (num_refined_cells) *num_refined_cells = ncell;
+  PMS_CATCH
+}
+
+// StructuredGridRefinerImpl::refine (structured/StructuredGridRefinerDef.hpp:88-222) for every block, on the device
+int pms_refine_structured_field(pms_ctx* coarse, const char* src_field, pms_ctx* c, const char* dst_field) {
+  PMS_TRY
+  if (!coarse) throw PmsError(PMS_ERR_ARG, "null coarse ctx");
+  require_committed(coarse);
+  require_committed(c);
+  if (!coarse->structured || !c->structured || coarse->blocks.size() != c->blocks.size())
+    throw PmsError(PMS_ERR_ARG, "refiner: grids do not match");
+  if (coarse->device != c->device) throw PmsError(PMS_ERR_ARG, "refiner: both grids must live on the same GPU");
+  DField& fi = coarse->field(src_field);
+  DField& fo = c->field(dst_field);
+  if (fi.ncomp != 3 || fo.ncomp != 3) throw PmsError(PMS_ERR_ARG, "refiner prolongs 3-component nodal fields");
+  for (size_t ib = 0; ib < c->blocks.size(); ib++)
+    for (int d = 0; d < 3; d++)
+      if (c->blocks[ib].n[d] != 2 * coarse->blocks[ib].n[d] - 1)
+        throw PmsError(PMS_ERR_ARG, "refiner: output block is not the 2x refinement of the input block");
+  PMS_CUDA(cudaSetDevice(c->device));
+  if (coarse->stream != c->stream) {  // order after everything queued on the coarse grid's stream
+    cudaEvent_t ev;
+    PMS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    PMS_CUDA(cudaEventRecord(ev, coarse->stream));
+    PMS_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
+    PMS_CUDA(cudaEventDestroy(ev));
+  }
+  for (size_t ib = 0; ib < c->blocks.size(); ib++) {
+    const HBlock& bi = coarse->blocks[ib];
+    const HBlock& bo = c->blocks[ib];
+    Timed t(c, FAM_REFINE);
+    c->L->refine_sgrid(c->stream, (int)bi.n[0], (int)bi.n[1], (int)bi.n[2], fi.d, bi.off, coarse->Npad, fo.d, bo.off, c->Npad);
+    check_launch(c, "refine_sgrid");
+  }
+  fo.version++;
+  if (coarse->stream != c->stream) {  // the coarse grid may be freed or overwritten right after this call returns
+    cudaEvent_t ev;
+    PMS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    PMS_CUDA(cudaEventRecord(ev, c->stream));
+    PMS_CUDA(cudaStreamWaitEvent(coarse->stream, ev, 0));
+    PMS_CUDA(cudaEventDestroy(ev));
+  }
+  PMS_CATCH
+}
+
 int pms_nodal_field_axpby(pms_ctx* c, double alpha, const char* x, double beta, const char* y) {
   PMS_TRY
   require_committed(c);
@@ -1804,7 +1886,7 @@ int pms_synchronize(pms_ctx* c) {
   PMS_CATCH
 }
 static int family_of(const std::string& f) {
-  const char* names[FAM_COUNT] = {"metric", "gradient", "blas1", "update", "alpha0", "edge", "halo"};
+  const char* names[FAM_COUNT] = {"metric", "gradient", "blas1", "update", "alpha0", "edge", "halo", "refine"};
   for (int i = 0; i < FAM_COUNT; i++)
     if (f == names[i]) return i;
   return -1;

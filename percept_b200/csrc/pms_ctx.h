@@ -46,7 +46,7 @@ struct DField {
   uint64_t version = 0;  // bumped on every write; keys the metric cache
 };
 
-enum Family { FAM_METRIC = 0, FAM_GRADIENT, FAM_BLAS1, FAM_UPDATE, FAM_ALPHA0, FAM_EDGE, FAM_HALO, FAM_COUNT };
+enum Family { FAM_METRIC = 0, FAM_GRADIENT, FAM_BLAS1, FAM_UPDATE, FAM_ALPHA0, FAM_EDGE, FAM_HALO, FAM_REFINE, FAM_COUNT };
 
 struct pms_ctx {
   int device = 0;

@@ -1693,6 +1693,73 @@ __global__ void __launch_bounds__(NT) k_elem_fixed_bits(const MeshDev m, const u
     bits[m.elem_off + e] = (uint8_t)b;
   }
 }
+// ------------------------------------------------------------------------------------------------
+// StructuredGridRefiner 2x prolongation (structured/StructuredGridRefinerDef.hpp:134-222).  The reference loops over
+// INPUT nodes and writes the vertex, 3 edge midpoints, 3 face centres and the centroid each one owns; here one thread
+// per OUTPUT node (coalesced 8-byte stores, the coarse reads hit L1/L2): its index parity says which of the four it is,
+// and the coarse nodes are summed in the reference's order (i outermost, k innermost; 0.5*(a+b) for edges).  HBM-bound:
+// 24 B read per coarse node + 24 B written per fine node.
+// ------------------------------------------------------------------------------------------------
+// fine node of parity (pi, PJ, PK) from the 2x2x2 coarse values xv[a][b][c]: i outermost / k innermost as in the
+// reference's loops, 0.5*(a+b) for edge midpoints, plain copy for vertices
+template <int PJ, int PK>
+__device__ __forceinline__ double refine_value(const double (&xv)[2][2][2], const int pi) {
+  if (PJ + PK == 0) return pi ? 0.5 * (xv[0][0][0] + xv[1][0][0]) : xv[0][0][0];
+  if (PJ + PK == 1 && !pi) return 0.5 * (xv[0][0][0] + xv[0][PJ][PK]);
+  const double wgt = (PJ + PK + pi) == 2 ? 0.25 : 0.125;
+  double v = 0.0;
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    if (a > pi) break;
+#pragma unroll
+    for (int b = 0; b <= PJ; b++)
+#pragma unroll
+      for (int c = 0; c <= PK; c++) v += wgt * xv[a][b][c];
+  }
+  return v;
+}
+
+// One thread per (fine I, coarse j) of coarse plane k = blockIdx.y: it loads the <= 8 coarse values once and writes the
+// up to four fine nodes (I, 2j + {0,1}, 2k + {0,1}); stores stay coalesced along I, 32-bit index arithmetic only.
+__global__ void __launch_bounds__(NT) k_refine_sgrid(const int ni, const int nj, const int nk, const double* __restrict__ src,
+                                                     const long long src_stride, double* __restrict__ dst,
+                                                     const long long dst_stride) {
+  const unsigned oi = 2 * ni - 1, oj = 2 * nj - 1;
+  const unsigned t = blockIdx.x * NT + threadIdx.x, k = blockIdx.y;
+  if (t >= oi * (unsigned)nj) return;
+  const unsigned j = t / oi, I = t - j * oi;
+  const int pi = I & 1;
+  const bool hj = j + 1 < (unsigned)nj, hk = k + 1 < (unsigned)nk;
+  const long long dj = ni, dk = (long long)ni * nj;
+  const long long base = (I >> 1) + dj * j + dk * k;
+  const long long o = I + (long long)oi * (2 * j + (long long)oj * 2 * k), odj = oi, odk = (long long)oi * oj;
+#pragma unroll
+  for (int ic = 0; ic < 3; ic++) {
+    const double* x = src + ic * src_stride + base;
+    double xv[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+          xv[a][b][c] = (a <= pi && (b == 0 || hj) && (c == 0 || hk)) ? __ldg(x + a + b * dj + c * dk) : 0.0;
+    double* y = dst + ic * dst_stride + o;
+    y[0] = refine_value<0, 0>(xv, pi);
+    if (hj) y[odj] = refine_value<1, 0>(xv, pi);
+    if (hk) y[odk] = refine_value<0, 1>(xv, pi);
+    if (hj && hk) y[odj + odk] = refine_value<1, 1>(xv, pi);
+  }
+}
+
+static void launch_refine_sgrid(cudaStream_t st, int ni, int nj, int nk, const double* src, long long src_off, long long src_stride,
+                                double* dst, long long dst_off, long long dst_stride) {
+  const long long oi = 2LL * ni - 1;
+  // limits: (2ni-1)*nj below 2^32, at most 65535 coarse planes (inside the 2^31-node ctx limit for any sane block)
+  k_refine_sgrid<<<dim3((unsigned)((oi * nj + NT - 1) / NT), (unsigned)nk), NT, 0, st>>>(ni, nj, nk, src + src_off, src_stride,
+                                                                                       dst + dst_off, dst_stride);
+}
+
 static void launch_elem_fixed_bits(cudaStream_t st, const MeshDev& m, const uint8_t* fixed, uint8_t* bits) {
   if (m.kind == KIND_SGRID)
     k_elem_fixed_bits<FL_SGRID><<<elem_grid<FL_SGRID>(m), NT, 0, st>>>(m, fixed, bits);
@@ -1706,7 +1773,8 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_group_sum, launch_axpby,         launch_axpbypgz,    launch_set,
                                       launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,
-                                      launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_shared_sum};
+                                      launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_shared_sum,
+                                      launch_refine_sgrid};
 
 const Launchers* launchers() { return &g_launchers; }
 void set_variant(int metric_corners, int grad_corners) {

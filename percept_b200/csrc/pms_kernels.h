@@ -127,6 +127,10 @@ struct Launchers {
   // cross-rank interface sum (structured block per GPU), ascending rank order
   void (*shared_sum)(cudaStream_t, long long nshared, const int32_t* nodes, const int64_t* ptr, const int64_t* ent_pos,
                      const int32_t* ent_cnt, const double* recvbuf, double* f, int ncomp, long long stride);
+  // StructuredGridRefiner: 2x prolongation of a 3-component nodal field of one block (coarse ni x nj x nk nodes at
+  // src + src_off, component stride src_stride) onto the (2ni-1) x (2nj-1) x (2nk-1) block at dst + dst_off
+  void (*refine_sgrid)(cudaStream_t, int ni, int nj, int nk, const double* src, long long src_off, long long src_stride,
+                       double* dst, long long dst_off, long long dst_stride);
 };
 
 }  // namespace pmsk

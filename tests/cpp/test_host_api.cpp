@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <string>
 #include <vector>
 
 #include "percept_b200/ReferenceMeshSmootherConjugateGradient.hpp"
@@ -90,6 +92,61 @@ int main() {
     for (size_t i = 0; i < 3 * N; i++) maxd = std::fmax(maxd, std::fabs(x[i] - w[i]));
     EXPECT_NEAR(maxd, 0.0, 0.02 / nele);
     std::remove("smootherlogperturbed_25x25x25.txt");
+  }
+  {  // TEST(regr_PerceptCGNS, test6_sgrid_refine) (RegressionTestPerceptCGNS.cpp:409-429): fixture -> refine -> smooth,
+     // and the refine-then-smooth set-up of SGridSmootherMultiBlockvsSingleBlock.cpp:150-175
+    PerceptMesh eMesh(3u);
+    std::array<unsigned, 3> sizes{{4, 4, 4}};
+    std::shared_ptr<BlockStructuredGrid> bsg = BlockStructuredGrid::fixture_1(sizes);
+    bsg->m_sblocks[0]->dump_vtk("cube", 0, 1);
+    StructuredGridRefiner sgr1(bsg, 0);
+    sgr1.m_input->dump_vtk("cube_init");
+    const unsigned ncell = sgr1.do_refine();
+    sgr1.m_output->dump_vtk("cube_ref");
+    EXPECT_EQ(ncell, 6u * 6u * 6u);
+    EXPECT_EQ(sgr1.m_output->m_sblocks[0]->node_size[0], 7u);
+    EXPECT_EQ(sgr1.m_output->m_sblocks[0]->m_boundaryConditions[1].beg[0], 7);  // imax face: 4 -> 7
+    EXPECT_EQ(sgr1.m_output->m_sblocks[0]->m_boundaryConditions[5].end[2], 7);
+    StructuredGridRefiner sgr2(sgr1.m_output, 0);  // refine again: 13^3 nodes
+    EXPECT_EQ(sgr2.do_refine(), 12u * 12u * 12u);
+    bsg = sgr2.m_output;
+    {  // twice-refined fixture == finer fixture (edge/face/centroid averages of a uniform lattice)
+      auto fine = BlockStructuredGrid::fixture_1({{13, 13, 13}});
+      double maxd = 0;
+      for (size_t i = 0; i < fine->m_sblocks[0]->m_sgrid_coords.size(); i++)
+        maxd = std::fmax(maxd, std::fabs(fine->m_sblocks[0]->m_sgrid_coords[i] - bsg->m_sblocks[0]->m_sgrid_coords[i]));
+      EXPECT_NEAR(maxd, 0.0, 2.3e-16);
+    }
+    // do_smooth_block_structured (RegressionTestPerceptCGNS.cpp:381-407): perturb the interior, smooth with fixed boundary
+    eMesh.set_block_structured_grid(bsg);
+    eMesh.add_coordinate_state_fields();
+    const size_t N = eMesh.num_nodes_local();
+    std::vector<double> x(3 * N);
+    eMesh.get_field("coordinates", x.data());
+    eMesh.set_field("coordinates_NM1", x.data());
+    pms_fixture_perturb_rand(13, 13, 13, 0.25 / 12, 1, x.data());
+    eMesh.set_field("coordinates", x.data());
+    eMesh.set_field("coordinates_N", x.data());
+    eMesh.setProperty("in_filename", "cube_ref");
+    SGridBoundarySelector boundarySelector(&eMesh);
+    ReferenceMeshSmootherConjugateGradientImpl<StructuredGrid> pmmpsi(&eMesh, NULL, &boundarySelector, 0, 200, 1.e-4, 1);
+    pmmpsi.run();
+    EXPECT_EQ(pmmpsi.m_num_invalid, (size_t)0);
+    std::vector<double> w(3 * N);
+    eMesh.get_field("coordinates", x.data());
+    eMesh.get_field("coordinates_NM1", w.data());
+    double maxd = 0;
+    for (size_t i = 0; i < 3 * N; i++) maxd = std::fmax(maxd, std::fabs(x[i] - w[i]));
+    EXPECT_NEAR(maxd, 0.0, 0.02 / 12);
+    std::printf("sgrid_refine: 3^3 -> 6^3 -> 12^3 cells, smoothed back to the lattice within %.2e\n", maxd);
+    // the .vts piece is the reference's ASCII layout: header + one "%16.4f" triple per node
+    std::ifstream vts("cube_ref.0.vts");
+    std::string line;
+    std::getline(vts, line);
+    EXPECT_EQ(line.find("<VTKFile type=\"StructuredGrid\"") == 0, true);
+    std::getline(vts, line);
+    EXPECT_EQ(line.find("WholeExtent=\"0 6 0 6 0 6\"") != std::string::npos, true);
+    for (const char* f : {"cube.0.vts", "cube_init.pvd", "cube_init.0.vts", "cube_ref.pvd", "cube_ref.0.vts", "smootherlogcube_ref.txt"}) std::remove(f);
   }
   {  // error convention: failures surface as std::runtime_error
     bool threw = false;

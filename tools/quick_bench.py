@@ -27,7 +27,7 @@ def run(kind, nele, eps, reps=5):
     s = 1e-3 / nele * np.random.default_rng(0).standard_normal((3, nnod)); c.upload("cg_s", s)
     c.set_timing(1)
     ops = os.environ.get("QB_OPS", "metric0,metricA,mgrad").split(",")
-    for stage in [int(v) for v in os.environ.get("QB_STAGES", "0,1").split(",")]:
+    for stage in [int(v) for v in os.environ.get("QB_STAGES", "0,1").split(",") if v != ""]:
         for what in ops:
             for it in range(reps + 2):
                 if it == 2: c.kernel_time_reset()
@@ -41,6 +41,16 @@ def run(kind, nele, eps, reps=5):
             extra = 0 if kind == "sgrid" else (32 if kind == "hex8" else 16) * ne
             gb = (bpn * nnod + extra) / 1e9
             print(f"stage {stage} {what:8s}: {ms:8.3f} ms  {ne/ms/1e6:8.2f} Gelem/s  alg {gb/ms*1e3:7.1f} GB/s ({gb/ms*1e3/6561.6*100:5.1f}% of 6561.6)")
+    if kind == "sgrid" and "refine" in os.environ.get("QB_OPS", "refine"):
+        # StructuredGridRefiner prolongation: nele^3 -> (2 nele)^3 cells
+        f = pb.create(); c.refine_topology(f); f.commit(); f.set_timing(1)
+        for it in range(reps + 2):
+            if it == 2: f.kernel_time_reset()
+            c.refine_field("coordinates", f, "coordinates")
+        ms, n = f.kernel_time_ms("refine"); ms /= reps
+        gb = 24 * (nnod + f.num_nodes_local) / 1e9
+        print(f"refine {nele}^3 -> {2*nele}^3: {ms:8.3f} ms  {f.num_nodes_local/ms/1e6:8.2f} Gnode/s  alg {gb/ms*1e3:7.1f} GB/s ({gb/ms*1e3/6561.6*100:5.1f}% of 6561.6)")
+        f.close()
     if os.environ.get("QB_OPS"): c.close(); return
     # BLAS-1 style kernels
     for name, fn, bpn in (("dot", lambda: c.dot("cg_s", "cg_g"), 48), ("axpby", lambda: c.axpby(1.0, "cg_g", 0.5, "cg_s"), 72),
