@@ -153,7 +153,47 @@ struct STKSelector {  // stands for stk::mesh::Selector evaluated on node bucket
   std::function<bool(size_t node)> pred;
   bool operator()(size_t node) const { return pred(node); }
 };
-class MeshGeometry;  // CAD hooks (classify_node / normal_at / snap): pointer kept in the API, must be null on this path
+// MeshGeometry (mesh/geometry/kernel/MeshGeometry.hpp:155-265): the reference classifies nodes against CAD entities
+// (classify_node -> dof 0 vertex / 1 curve / 2 surface / 3 volume + evaluator) and evaluates normal_at /
+// snap_points_to_geometry through an OpenNURBS / PGEOM kernel.  Here the geometry is a set of analytic surfaces
+// evaluated on the GPU and the classification is handed over per node.
+class MeshGeometry {
+ public:
+  struct Surface {
+    int kind;
+    double params[7];
+  };
+  int add_plane(const std::array<double, 3>& point, const std::array<double, 3>& normal) {
+    return add(PMS_SURF_PLANE, {{point[0], point[1], point[2], normal[0], normal[1], normal[2], 0.0}});
+  }
+  int add_sphere(const std::array<double, 3>& centre, double radius) {
+    return add(PMS_SURF_SPHERE, {{centre[0], centre[1], centre[2], radius, 0.0, 0.0, 0.0}});
+  }
+  int add_cylinder(const std::array<double, 3>& axis_point, const std::array<double, 3>& axis_dir, double radius) {
+    return add(PMS_SURF_CYLINDER, {{axis_point[0], axis_point[1], axis_point[2], axis_dir[0], axis_dir[1], axis_dir[2], radius}});
+  }
+  // dof[n] as classify_node returns it, evaluator[n] = surface id of dof-2 nodes
+  void set_classification(const std::vector<int8_t>& dof, const std::vector<int32_t>& evaluator) {
+    m_dof = dof;
+    m_evaluator = evaluator;
+  }
+  int classify_node(size_t node, size_t& curveOrSurfaceEvaluator) const {
+    curveOrSurfaceEvaluator = node < m_evaluator.size() && m_evaluator[node] >= 0 ? (size_t)m_evaluator[node] : 0;
+    return node < m_dof.size() ? (int)m_dof[node] : 3;
+  }
+  std::vector<Surface> m_surfaces;
+  std::vector<int8_t> m_dof;
+  std::vector<int32_t> m_evaluator;
+
+ private:
+  int add(int kind, const std::array<double, 7>& p) {
+    Surface s;
+    s.kind = kind;
+    for (int i = 0; i < 7; i++) s.params[i] = p[i];
+    m_surfaces.push_back(s);
+    return (int)m_surfaces.size() - 1;
+  }
+};
 
 struct StructuredGrid {
   typedef SGridSelector MTSelector;
@@ -189,7 +229,12 @@ class PerceptMesh {
   pms_ctx* ctx() const { return m_ctx; }
   int get_spatial_dim() const { return m_spatial_dim; }
   int get_rank() const { return m_rank; }
-  bool get_smooth_surfaces() const { return false; }  // surface smoothing needs CAD queries: out of scope
+  // mesh_adapt --smooth_surfaces (PerceptMesh.hpp: get/set_smooth_surfaces): MS_SURFACE nodes slide on their surface
+  bool get_smooth_surfaces() const { return m_smooth_surfaces; }
+  void set_smooth_surfaces(bool v) {
+    m_smooth_surfaces = v;
+    check(m_ctx, pms_set_option(m_ctx, "smooth_surfaces", v ? 1.0 : 0.0));
+  }
 
   // string property map (PerceptMesh.hpp:737-738)
   void setProperty(const std::string& k, const std::string& v) { m_props[k] = v; }
@@ -269,7 +314,7 @@ class PerceptMesh {
  private:
   pms_ctx* m_ctx = nullptr;
   int m_spatial_dim, m_rank = 0;
-  bool m_committed = false, m_has_bulk = false;
+  bool m_committed = false, m_has_bulk = false, m_smooth_surfaces = false;
   std::shared_ptr<BlockStructuredGrid> m_bsg;
   std::map<std::string, std::string> m_props;
 };
@@ -374,8 +419,6 @@ class MeshSmootherImpl {  // MeshSmoother.hpp:35-80
                    int parallelIterations_ = 20)
       : m_eMesh(eMesh), innerIter(innerIter_), gradNorm(gradNorm_), parallelIterations(parallelIterations_),
         m_stk_boundarySelector(stk_select), m_sgrid_boundarySelector(sgrid_select), m_meshGeometry(meshGeometry) {
-    if (meshGeometry)
-      throw std::runtime_error("percept_b200: MeshGeometry (CAD classify/snap) is not data-parallel and is outside this path; pass 0");
   }
   virtual ~MeshSmootherImpl() {}
   StructuredGrid::MTSelector* get_sgrid_select() const { return m_sgrid_boundarySelector; }
@@ -402,12 +445,41 @@ class MeshSmootherImpl {  // MeshSmoother.hpp:35-80
       bool f = (*m_stk_boundarySelector)(node);
       return std::make_pair(f, f ? (int)MS_ON_BOUNDARY : (int)MS_NOT_ON_BOUNDARY);
     }
-    return std::make_pair(false, (int)MS_VOLUME);
+    return geometry_fixed_flag(m_meshGeometry, node);
   }
 
  protected:
+  // classification branch of get_fixed_flag (MeshSmoother.cpp:293-340)
+  std::pair<bool, int> geometry_fixed_flag(MeshGeometry* geom, size_t node) {
+    if (!geom) return std::make_pair(false, (int)MS_VOLUME);
+    size_t evaluator = 0;
+    const int dof = geom->classify_node(node, evaluator);
+    if (dof == 0) return std::make_pair(true, (int)MS_VERTEX);
+    if (dof == 1) return std::make_pair(true, (int)MS_CURVE);
+    if (dof == 2) return std::make_pair(!m_eMesh->get_smooth_surfaces(), (int)MS_SURFACE);
+    return std::make_pair(false, (int)MS_VOLUME);
+  }
+  std::pair<bool, int> geometry_fixed_flag(SGridMeshGeometry*, size_t) { return std::make_pair(false, (int)MS_VOLUME); }
+  void upload_geometry(MeshGeometry* geom) {  // surfaces + classification -> device (fixed mask derived there)
+    for (auto& s : geom->m_surfaces) check(m_eMesh->ctx(), pms_add_analytic_surface(m_eMesh->ctx(), s.kind, s.params, nullptr));
+    const size_t N = m_eMesh->num_nodes_local();
+    std::vector<int8_t> dof(N, 3);
+    std::vector<int32_t> ev(N, -1);
+    for (size_t n = 0; n < N; n++) {
+      size_t e = 0;
+      dof[n] = (int8_t)geom->classify_node(n, e);
+      if (dof[n] == 2) ev[n] = (int32_t)e;
+    }
+    check(m_eMesh->ctx(), pms_set_node_classification(m_eMesh->ctx(), dof.data(), ev.data()));
+  }
+  void upload_geometry(SGridMeshGeometry*) {}
+
   // the selectors are evaluated once on the host into the device fixed mask
   void upload_fixed_mask() {
+    if (!m_stk_boundarySelector && !m_sgrid_boundarySelector && m_meshGeometry && !m_eMesh->get_block_structured_grid()) {
+      upload_geometry(m_meshGeometry);
+      return;
+    }
     const size_t N = m_eMesh->num_nodes_local();
     std::vector<uint8_t> mask(N, 0);
     auto bsg = m_eMesh->get_block_structured_grid();
@@ -525,8 +597,16 @@ class ReferenceMeshSmootherConjugateGradientImpl : public ReferenceMeshSmootherB
     return a;
   }
   void get_edge_lengths(PerceptMesh* /*eMesh*/) { check(ctx(), pms_get_edge_lengths(ctx())); }  // Def.hpp:759-771
-  void get_surface_normals(PerceptMesh*) {}  // only with smooth_surfaces
-  void snap_nodes() {}                       // only with smooth_surfaces
+  // get_surface_normals (Def.hpp:596-706): normals at non-fixed surface nodes, SoA (3, N), zero elsewhere
+  std::vector<double> m_surface_normals;
+  void get_surface_normals(PerceptMesh* eMesh) {
+    m_surface_normals.assign(3 * eMesh->num_nodes_local(), 0.0);
+    check(ctx(), pms_get_surface_normals(ctx(), m_surface_normals.data()));
+  }
+  void snap_nodes() {  // Def.hpp:273-316 (STKMesh); the StructuredGrid specialisation is empty in the reference too
+    if (this->m_eMesh->get_block_structured_grid()) return;
+    check(ctx(), pms_snap_nodes(ctx(), nullptr));
+  }
 
   virtual bool check_convergence() {  // Def.hpp:989-1008
     pms_state st;

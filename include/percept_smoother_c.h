@@ -199,6 +199,28 @@ int pms_set_interface(pms_ctx* ctx, int n_neighbors, const int* neighbor_ranks, 
 int pms_halo_exchange(pms_ctx* ctx, const char* name);
 
 /* ---- instrumentation --------------------------------------------------------- */
+/* ---- surface smoothing hooks ------------------------------------------------------------------------
+ * The reference's `smooth_surfaces` branch (mesh_adapt --smooth_surfaces=1) lets nodes classified on a CAD surface move
+ * along it: get_fixed_flag (mesh/mod/smoother/MeshSmoother.cpp:271-344) un-fixes MS_SURFACE nodes, get_gradient_2
+ * projects cg_g onto the tangent plane at those nodes (ReferenceMeshSmootherConjugateGradientDef.hpp:1401-1447 +
+ * MeshSmoother.cpp:437-460), and run_one_iteration re-snaps them after the update and rejects an invalid result
+ * ("bad mesh after snap_node_positions...", Def.hpp:1078-1089, snap_nodes :236-316).  The CAD evaluators
+ * (MeshGeometry::{classify_node, normal_at, snap_points_to_geometry}, OpenNURBS/PGEOM) are third party; here the
+ * caller hands over the classification and analytic evaluators instead:
+ *   pms_add_analytic_surface(kind, params): PMS_SURF_PLANE  params = point[3], normal[3]
+ *                                           PMS_SURF_SPHERE params = centre[3], radius
+ *                                           PMS_SURF_CYLINDER params = axis point[3], axis direction[3], radius
+ *   pms_set_node_classification(dof, surface_id): per local node, dof as classify_node returns it (0 vertex, 1 curve,
+ *     2 surface, 3 volume) and the surface evaluator of dof-2 nodes.  Replaces the boundary-selector fixed mask:
+ *     dof 0/1 fixed, dof 2 fixed unless option "smooth_surfaces" is 1, dof 3 free.  Unstructured meshes only
+ *     (the reference's StructuredGrid specialisation is "not impl").  Call after pms_commit.
+ *   pms_snap_nodes(&dmax): snap_nodes() on its own; pms_get_surface_normals(out SoA (3,N)): get_surface_normals().   */
+enum { PMS_SURF_PLANE = 0, PMS_SURF_SPHERE = 1, PMS_SURF_CYLINDER = 2 };
+int pms_add_analytic_surface(pms_ctx* ctx, int kind, const double* params, int* surface_id);
+int pms_set_node_classification(pms_ctx* ctx, const int8_t* dof, const int32_t* surface_id);
+int pms_snap_nodes(pms_ctx* ctx, double* dmax);
+int pms_get_surface_normals(pms_ctx* ctx, double* host_out);
+
 /* ---- structured 2x refinement feeding the smoother -------------------------------------------------
  * Replaces StructuredGridRefiner::do_refine (structured/StructuredGridRefiner.cpp:40-170, .hpp:19-52) and
  * StructuredGridRefinerImpl::refine (structured/StructuredGridRefinerDef.hpp:43-226).

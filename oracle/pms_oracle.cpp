@@ -544,6 +544,16 @@ struct orc_ctx {
   std::map<std::string, Field> fields;
   bool use_ref_mesh = true, real_is_double = false, adj_fixed = false;
   int omp_threads = 1;
+  // surface smoothing hooks: node classification as MeshGeometry::classify_node returns it
+  // (0 vertex, 1 curve, 2 surface, 3 volume) + the evaluator (analytic surface) of each surface node
+  bool smooth_surfaces = false;
+  struct Surface {
+    int kind;       // 0 plane (p, n), 1 sphere (c, R), 2 cylinder (a, u, R)
+    double p[3], u[3], R;
+  };
+  std::vector<Surface> surfaces;
+  std::vector<int8_t> node_dof;
+  std::vector<int32_t> node_surf;
   std::vector<double> elem_metric;
   std::vector<int32_t> elem_flag;
   std::string err;
@@ -551,6 +561,44 @@ struct orc_ctx {
 };
 
 namespace {
+
+// Analytic stand-ins for MeshGeometry::normal_at / snap_points_to_geometry (mesh/geometry/kernel/MeshGeometry.hpp:155-265;
+// the reference evaluates OpenNURBS / PGEOM CAD, third party and absent here).  Plain double arithmetic, left to right.
+inline void surf_normal(const orc_ctx::Surface& s, const double x[3], double n[3], double* t_out = nullptr) {
+  if (s.kind == 0) {
+    for (int i = 0; i < 3; i++) n[i] = s.u[i];
+    return;
+  }
+  double d[3] = {x[0] - s.p[0], x[1] - s.p[1], x[2] - s.p[2]};
+  if (s.kind == 2) {
+    const double t = d[0] * s.u[0] + d[1] * s.u[1] + d[2] * s.u[2];
+    for (int i = 0; i < 3; i++) d[i] = d[i] - t * s.u[i];
+    if (t_out) *t_out = t;
+  }
+  const double r = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  for (int i = 0; i < 3; i++) n[i] = r > 0.0 ? d[i] / r : 0.0;
+}
+inline void surf_snap(const orc_ctx::Surface& s, double x[3]) {
+  double n[3], t = 0.0;
+  surf_normal(s, x, n, &t);
+  if (s.kind == 0) {
+    const double h = (x[0] - s.p[0]) * n[0] + (x[1] - s.p[1]) * n[1] + (x[2] - s.p[2]) * n[2];
+    for (int i = 0; i < 3; i++) x[i] = x[i] - h * n[i];
+  } else if (s.kind == 1) {
+    for (int i = 0; i < 3; i++) x[i] = s.p[i] + s.R * n[i];
+  } else {
+    for (int i = 0; i < 3; i++) x[i] = (s.p[i] + t * s.u[i]) + s.R * n[i];
+  }
+}
+// get_fixed_flag with a geometry and no boundary selector (MeshSmoother.cpp:293-340)
+inline void apply_classification(orc_ctx& c) {
+  if (c.node_dof.empty()) return;
+  c.fixed.assign(c.node_dof.size(), 0);
+  for (size_t n = 0; n < c.node_dof.size(); n++) {
+    const int dof = c.node_dof[n];
+    c.fixed[n] = (dof == 0 || dof == 1 || (dof == 2 && !c.smooth_surfaces)) ? 1 : 0;
+  }
+}
 
 struct OrcError : std::runtime_error {
   int code;
@@ -869,7 +917,36 @@ struct Smoother {
           }
       }
       copy_field(c, "cg_r", "cg_g");
+      if (c.smooth_surfaces && !c.node_dof.empty())  // GenericAlgorithm_get_gradient_2, Def.hpp:1401-1447
+        for (size_t n = 0; n < c.N; n++) {
+          if (c.fixed[n] || c.node_dof[n] != 2) continue;
+          double x[3] = {X[n], X[c.N + n], X[2 * c.N + n]}, nrm[3];
+          surf_normal(c.surfaces.at(c.node_surf[n]), x, nrm);
+          double dot = 0.0;  // project_delta_to_tangent_plane, MeshSmoother.cpp:437-460
+          for (int i = 0; i < 3; i++) dot += g[i * c.N + n] * nrm[i];
+          for (int i = 0; i < 3; i++) g[i * c.N + n] -= dot * nrm[i];
+        }
     }
+  }
+
+  // snap_nodes (Def.hpp:236-316): non-fixed MS_SURFACE nodes go back onto their surface; returns max displacement
+  double snap_nodes() {
+    double dmax = 0.0;
+    if (c.node_dof.empty()) return dmax;
+    double* X = c.f("coordinates");
+    for (size_t n = 0; n < c.N; n++) {
+      if (c.fixed[n] || c.node_dof[n] != 2) continue;
+      double x[3] = {X[n], X[c.N + n], X[2 * c.N + n]};
+      const double o[3] = {x[0], x[1], x[2]};
+      surf_snap(c.surfaces.at(c.node_surf[n]), x);
+      double dm = 0.0;
+      for (int i = 0; i < 3; i++) {
+        dm += (o[i] - x[i]) * (o[i] - x[i]);
+        X[i * c.N + n] = x[i];
+      }
+      dmax = std::max(dmax, std::sqrt(dm));
+    }
+    return dmax;
   }
 
   // ---- edge lengths ----
@@ -1134,6 +1211,14 @@ struct Smoother {
     m_grad_norm_scaled = m_alpha_0 * std::sqrt(snorm) / Real(m_num_nodes);
     m_alpha = alpha;
     coord_update(alpha, true, m_dmax, m_dmax_relative);  // update_node_positions, Def.hpp:395-410
+    if (c.smooth_surfaces) {  // check if re-snapped geometry is acceptable, Def.hpp:1078-1089
+      snap_nodes();
+      if (m_stage != 0) {
+        bool total_valid_0 = true;
+        tm(0.0, total_valid_0);
+        if (!total_valid_0) throw OrcError(3, "bad mesh after snap_node_positions...");
+      }
+    }
     Real t = tm(0.0, total_valid);
     return t;
   }
@@ -1276,6 +1361,10 @@ int orc_set_option(orc_ctx* c, const char* key, double v) {
     c->real_is_double = v != 0;
   else if (k == "omp_threads")
     c->omp_threads = (int)v;
+  else if (k == "smooth_surfaces") {
+    c->smooth_surfaces = v != 0;
+    apply_classification(*c);
+  }
   else if (k == "strict_fp" || k == "cache_metric" || k == "keep_element_metrics")
     ;
   else {
@@ -1654,6 +1743,56 @@ int orc_refine_structured_field(orc_ctx* coarse, const char* src_field, orc_ctx*
                   for (unsigned cc = 0; cc < 2; cc++) o += 0.125 * in(i + a, j + b, k + cc, ic);
             }
         }
+  }
+  ORC_CATCH
+}
+
+// ---- surface smoothing hooks --------------------------------------------------------------------------
+int orc_add_analytic_surface(orc_ctx* c, int kind, const double* params, int* surface_id) {
+  ORC_TRY
+  if (kind < 0 || kind > 2) throw OrcError(2, "unknown analytic surface kind");
+  orc_ctx::Surface s{};
+  s.kind = kind;
+  for (int i = 0; i < 3; i++) s.p[i] = params[i];
+  if (kind == 1) {
+    s.R = params[3];
+  } else {
+    const double l = std::sqrt(params[3] * params[3] + params[4] * params[4] + params[5] * params[5]);
+    if (!(l > 0.0)) throw OrcError(2, "analytic surface: zero direction");
+    for (int i = 0; i < 3; i++) s.u[i] = params[3 + i] / l;
+    s.R = kind == 2 ? params[6] : 0.0;
+  }
+  c->surfaces.push_back(s);
+  if (surface_id) *surface_id = (int)c->surfaces.size() - 1;
+  ORC_CATCH
+}
+int orc_set_node_classification(orc_ctx* c, const int8_t* dof, const int32_t* surface_id) {
+  ORC_TRY
+  if (!c->committed || c->structured) throw OrcError(2, "node classification needs a committed unstructured mesh (sgrid: not impl)");
+  for (size_t n = 0; n < c->N; n++)
+    if (dof[n] == 2 && (surface_id[n] < 0 || surface_id[n] >= (int)c->surfaces.size())) throw OrcError(2, "surface node without a surface");
+  c->node_dof.assign(dof, dof + c->N);
+  c->node_surf.assign(surface_id, surface_id + c->N);
+  apply_classification(*c);
+  ORC_CATCH
+}
+int orc_snap_nodes(orc_ctx* c, double* dmax) {
+  ORC_TRY
+  Smoother<double> s(*c);
+  const double d = s.snap_nodes();
+  if (dmax) *dmax = d;
+  ORC_CATCH
+}
+// get_surface_normals (Def.hpp:596-706): normal at every non-fixed surface node, zero elsewhere; SoA (3, N)
+int orc_get_surface_normals(orc_ctx* c, double* out) {
+  ORC_TRY
+  const double* X = c->f("coordinates");
+  std::fill(out, out + 3 * c->N, 0.0);
+  for (size_t n = 0; n < c->N && !c->node_dof.empty(); n++) {
+    if (c->fixed[n] || c->node_dof[n] != 2) continue;
+    double x[3] = {X[n], X[c->N + n], X[2 * c->N + n]}, nrm[3];
+    surf_normal(c->surfaces.at(c->node_surf[n]), x, nrm);
+    for (int i = 0; i < 3; i++) out[i * c->N + n] = nrm[i];
   }
   ORC_CATCH
 }

@@ -80,6 +80,10 @@ class Api:
         "state_init": [C.POINTER(State)],
         "run_one_iteration": [C.POINTER(State), C.c_double, _dp],
         "run_algorithm": [C.c_int, C.c_double, C.c_char_p, C.POINTER(State)],
+        "add_analytic_surface": [C.c_int, _dp, C.POINTER(C.c_int)],
+        "set_node_classification": [C.c_void_p, C.c_void_p],
+        "snap_nodes": [_dp],
+        "get_surface_normals": [_dp],
         "refine_structured_topology": [C.c_void_p, C.POINTER(C.c_ulonglong)],
         "refine_structured_field": [C.c_char_p, C.c_void_p, C.c_char_p],
     }
@@ -199,6 +203,30 @@ class Ctx:
 
     def commit(self):
         self._call("commit")
+
+    # ---- surface smoothing hooks (MeshGeometry stand-ins) ----
+    def add_analytic_surface(self, kind, params):
+        """kind: 0 plane (point, normal), 1 sphere (centre, radius), 2 cylinder (axis point, axis dir, radius)."""
+        p = np.zeros(7)
+        p[:len(params)] = params
+        sid = C.c_int(-1)
+        self._call("add_analytic_surface", int(kind), _dptr(p), C.byref(sid))
+        return sid.value
+
+    def set_node_classification(self, dof, surface_id):
+        d = np.ascontiguousarray(dof, dtype=np.int8)
+        s = np.ascontiguousarray(surface_id, dtype=np.int32)
+        self._call("set_node_classification", d.ctypes.data, s.ctypes.data)
+
+    def snap_nodes(self):
+        d = C.c_double(0.0)
+        self._call("snap_nodes", C.byref(d))
+        return d.value
+
+    def get_surface_normals(self):
+        out = np.zeros((3, self.num_nodes_local))
+        self._call("get_surface_normals", _dptr(out))
+        return out
 
     # ---- StructuredGridRefiner (structured/StructuredGridRefiner.cpp:40-170) ----
     def refine_topology(self, fine):

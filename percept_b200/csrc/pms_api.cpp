@@ -588,6 +588,11 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write
   if (c->structured) interface_sum(c, G);  // block-per-GPU: complete the sums over ranks
   G.version++;
   if (!c->structured && write_r) Rr.version++;
+  if (c->smooth_surfaces && c->n_surf_nodes > 0) {  // GenericAlgorithm_get_gradient_2 (Def.hpp:1401-1447): after cg_r = cg_g
+    Timed t(c, FAM_GRADIENT);
+    c->L->surf_project(c->stream, c->n_surf_nodes, c->d_surf_nodes, c->d_surf_sid, c->d_surfaces, X.d, G.d, c->Npad);
+    check_launch(c, "surf_project");
+  }
   if (mtot) {
     fetch(c, 0, nb, nb);
     double m = 0.0;
@@ -668,6 +673,22 @@ void op_update(pms_ctx* c, double alpha, double* dmax, double* dmax_rel) {
   allreduce(c, v, 2, NCCL_MAX);
   *dmax = v[0];
   *dmax_rel = v[1];
+}
+
+// snap_nodes (Def.hpp:236-316): non-fixed MS_SURFACE nodes back onto their surface; returns the largest displacement
+double op_snap_nodes(pms_ctx* c) {
+  if (c->n_surf_nodes == 0) return 0.0;
+  DField& X = c->field("coordinates");
+  {
+    Timed t(c, FAM_UPDATE);
+    c->L->surf_snap(c->stream, c->n_surf_nodes, c->d_surf_nodes, c->d_surf_sid, c->d_surfaces, X.d, c->Npad, c->R, 0);
+    check_launch(c, "surf_snap");
+  }
+  X.version++;
+  fetch(c, 0, 1, 0);
+  double v[1] = {c->h_out_d[0]};
+  allreduce(c, v, 1, NCCL_MAX);
+  return v[0];
 }
 
 uint64_t op_count_invalid(pms_ctx* c) {  // MeshSmoother.cpp:192-234: untangle metric's valid flag
@@ -899,6 +920,14 @@ struct Driver {
     st->grad_norm_scaled = st->alpha_0 * std::sqrt(snorm) / double(st->num_nodes);
     st->alpha = alpha;
     op_update(c, alpha, &st->dmax, &st->dmax_relative);  // update_node_positions, Def.hpp:395-410
+    if (c->smooth_surfaces) {  // check if re-snapped geometry is acceptable, Def.hpp:1078-1089
+      op_snap_nodes(c);
+      if (st->stage != 0) {
+        bool total_valid_0 = true;
+        tm(0.0, total_valid_0);
+        if (!total_valid_0) throw PmsError(PMS_ERR_SMOOTHER, "bad mesh after snap_node_positions...");
+      }
+    }
     return tm(0.0, total_valid);
   }
 
@@ -1032,6 +1061,8 @@ void pms_destroy(pms_ctx* c) {
 
 const char* pms_last_error(const pms_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
 
+static void apply_classification(pms_ctx* c);
+
 int pms_set_option(pms_ctx* c, const char* key, double v) {
   PMS_TRY
   const std::string k(key);
@@ -1050,6 +1081,10 @@ int pms_set_option(pms_ctx* c, const char* key, double v) {
       c->d_elem_metric = dalloc<double>(c->Epad);
       c->d_elem_flag = dalloc<int32_t>(c->Epad);
     }
+  } else if (k == "smooth_surfaces") {  // PerceptMesh::get_smooth_surfaces (mesh_adapt --smooth_surfaces)
+    c->smooth_surfaces = v != 0;
+    if (c->committed) apply_classification(c);
+    invalidate_cache(c);
   } else if (k == "variant_metric_corners") {
     c->var_metric = (int)v;
     pms_fast::set_variant(c->var_metric, c->var_grad);
@@ -1132,6 +1167,33 @@ static void rebuild_skip_mask(pms_ctx* c) {
     skip[n] = (c->h_fixed[n] || (!c->h_node_owned.empty() && !c->h_node_owned[n])) ? 1 : 0;
   if (!c->d_skip) c->d_skip = dalloc<uint8_t>(c->Npad);
   PMS_CUDA(cudaMemcpy(c->d_skip, skip.data(), c->Npad, cudaMemcpyHostToDevice));
+}
+
+// get_fixed_flag with a geometry and no boundary selector (MeshSmoother.cpp:293-340): vertex / curve nodes fixed,
+// surface nodes fixed unless smooth_surfaces, volume nodes free; then the list of non-fixed surface nodes
+static void apply_classification(pms_ctx* c) {
+  if (c->h_node_dof.empty()) return;
+  std::vector<uint8_t> fx(c->N);
+  std::vector<int32_t> nodes, sid;
+  for (long long n = 0; n < c->N; n++) {
+    const int dof = c->h_node_dof[n];
+    fx[n] = (dof == 0 || dof == 1 || (dof == 2 && !c->smooth_surfaces)) ? 1 : 0;
+    if (dof == 2 && !fx[n]) {
+      nodes.push_back((int32_t)n);
+      sid.push_back(c->h_node_surf[n]);
+    }
+  }
+  if (pms_set_fixed_mask(c, fx.data()) != PMS_OK) throw PmsError(PMS_ERR_ARG, c->err);
+  for (void* p : {(void*)c->d_surf_nodes, (void*)c->d_surf_sid, (void*)c->d_surfaces})
+    if (p) cudaFree(p);
+  c->d_surf_nodes = c->d_surf_sid = nullptr;
+  c->d_surfaces = nullptr;
+  c->n_surf_nodes = (long long)nodes.size();
+  if (c->n_surf_nodes > 0) {
+    c->d_surf_nodes = dupload(nodes);
+    c->d_surf_sid = dupload(sid);
+    c->d_surfaces = dupload(c->h_surfaces);
+  }
 }
 
 static long long total_nodes_precommit(pms_ctx* c) {
@@ -1577,6 +1639,68 @@ int pms_refine_structured_field(pms_ctx* coarse, const char* src_field, pms_ctx*
     PMS_CUDA(cudaStreamWaitEvent(coarse->stream, ev, 0));
     PMS_CUDA(cudaEventDestroy(ev));
   }
+  PMS_CATCH
+}
+
+// ---- surface smoothing hooks ----------------------------------------------------------------------
+int pms_add_analytic_surface(pms_ctx* c, int kind, const double* params, int* surface_id) {
+  PMS_TRY
+  if (kind < PMS_SURF_PLANE || kind > PMS_SURF_CYLINDER || !params) throw PmsError(PMS_ERR_ARG, "unknown analytic surface kind");
+  pmsk::SurfaceDev s{};
+  s.kind = kind;
+  for (int i = 0; i < 3; i++) s.p[i] = params[i];
+  if (kind == PMS_SURF_SPHERE) {
+    s.R = params[3];
+  } else {
+    const double l = std::sqrt(params[3] * params[3] + params[4] * params[4] + params[5] * params[5]);
+    if (!(l > 0.0)) throw PmsError(PMS_ERR_ARG, "analytic surface: zero direction");
+    for (int i = 0; i < 3; i++) s.u[i] = params[3 + i] / l;
+    s.R = kind == PMS_SURF_CYLINDER ? params[6] : 0.0;
+  }
+  c->h_surfaces.push_back(s);
+  if (surface_id) *surface_id = (int)c->h_surfaces.size() - 1;
+  if (c->committed && !c->h_node_dof.empty()) apply_classification(c);
+  PMS_CATCH
+}
+
+int pms_set_node_classification(pms_ctx* c, const int8_t* dof, const int32_t* surface_id) {
+  PMS_TRY
+  require_committed(c);
+  // MeshSmootherImpl<StructuredGrid>::project_delta_to_tangent_plane is VERIFY_MSG("not impl") (MeshSmoother.cpp:462-467)
+  if (c->structured) throw PmsError(PMS_ERR_ARG, "surface smoothing of structured grids: not impl (as in the reference)");
+  if (!dof || !surface_id) throw PmsError(PMS_ERR_ARG, "null classification");
+  for (long long n = 0; n < c->N; n++)
+    if (dof[n] == 2 && (surface_id[n] < 0 || surface_id[n] >= (int)c->h_surfaces.size()))
+      throw PmsError(PMS_ERR_ARG, "surface node without a surface evaluator");
+  c->h_node_dof.assign(dof, dof + c->N);
+  c->h_node_surf.assign(surface_id, surface_id + c->N);
+  apply_classification(c);
+  PMS_CATCH
+}
+
+int pms_snap_nodes(pms_ctx* c, double* dmax) {
+  PMS_TRY
+  require_committed(c);
+  const double d = op_snap_nodes(c);
+  if (dmax) *dmax = d;
+  PMS_CATCH
+}
+
+int pms_get_surface_normals(pms_ctx* c, double* host_out) {
+  PMS_TRY
+  require_committed(c);
+  if (!host_out) throw PmsError(PMS_ERR_ARG, "null output");
+  double* d = dalloc<double>((size_t)3 * c->Npad);
+  PMS_CUDA(cudaMemsetAsync(d, 0, (size_t)3 * c->Npad * sizeof(double), c->stream));
+  if (c->n_surf_nodes > 0) {
+    Timed t(c, FAM_UPDATE);
+    c->L->surf_normals(c->stream, c->n_surf_nodes, c->d_surf_nodes, c->d_surf_sid, c->d_surfaces, c->field("coordinates").d, d, c->Npad);
+    check_launch(c, "surf_normals");
+  }
+  for (int k = 0; k < 3; k++)
+    PMS_CUDA(cudaMemcpyAsync(host_out + (size_t)k * c->N, d + (size_t)k * c->Npad, c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
   PMS_CATCH
 }
 

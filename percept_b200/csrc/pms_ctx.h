@@ -84,6 +84,15 @@ struct pms_ctx {
   double* d_elem_metric = nullptr;
   int32_t* d_elem_flag = nullptr;
 
+  // surface smoothing hooks: classification as MeshGeometry::classify_node gives it + analytic evaluators
+  bool smooth_surfaces = false;
+  std::vector<pmsk::SurfaceDev> h_surfaces;
+  std::vector<int8_t> h_node_dof;
+  std::vector<int32_t> h_node_surf;
+  pmsk::SurfaceDev* d_surfaces = nullptr;
+  int32_t *d_surf_nodes = nullptr, *d_surf_sid = nullptr;  // non-fixed MS_SURFACE nodes and their evaluator
+  long long n_surf_nodes = 0;
+
   std::map<std::string, DField> fields;
 
   // reductions

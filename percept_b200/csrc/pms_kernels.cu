@@ -1760,6 +1760,108 @@ static void launch_refine_sgrid(cudaStream_t st, int ni, int nj, int nk, const d
                                                                                        dst + dst_off, dst_stride);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Surface smoothing hooks: GenericAlgorithm_get_gradient_2 + project_delta_to_tangent_plane
+// (Def.hpp:1401-1447, MeshSmoother.cpp:437-460), snap_nodes (Def.hpp:236-316), get_surface_normals (Def.hpp:596-706)
+// with analytic evaluators in place of the CAD kernel.  One thread per listed (non-fixed, MS_SURFACE) node.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void surf_normal(const SurfaceDev& s, const double (&x)[3], double (&n)[3], double& t) {
+  t = 0.0;
+  if (s.kind == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) n[i] = s.u[i];
+    return;
+  }
+  double d[3] = {x[0] - s.p[0], x[1] - s.p[1], x[2] - s.p[2]};
+  if (s.kind == 2) {
+    t = d[0] * s.u[0] + d[1] * s.u[1] + d[2] * s.u[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) d[i] = d[i] - t * s.u[i];
+  }
+  const double r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+#pragma unroll
+  for (int i = 0; i < 3; i++) n[i] = r > 0.0 ? d[i] / r : 0.0;
+}
+
+__global__ void __launch_bounds__(NT) k_surf_project(const long long n, const int32_t* __restrict__ nodes,
+                                                     const int32_t* __restrict__ sid, const SurfaceDev* __restrict__ surfs,
+                                                     const double* __restrict__ x, double* __restrict__ g, const long long stride) {
+  const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+  if (i >= n) return;
+  const long long nd = nodes[i];
+  const SurfaceDev s = surfs[sid[i]];
+  const double xx[3] = {x[nd], x[stride + nd], x[2 * stride + nd]};
+  double nrm[3], t;
+  surf_normal(s, xx, nrm, t);
+  double gg[3] = {g[nd], g[stride + nd], g[2 * stride + nd]};
+  double dot = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) dot += gg[k] * nrm[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) g[k * stride + nd] = gg[k] - dot * nrm[k];
+}
+
+__global__ void __launch_bounds__(NT) k_surf_snap(const long long n, const int32_t* __restrict__ nodes, const int32_t* __restrict__ sid,
+                                                  const SurfaceDev* __restrict__ surfs, double* __restrict__ x, const long long stride,
+                                                  const Reduce R, const int slot) {
+  double v[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    const long long nd = nodes[i];
+    const SurfaceDev s = surfs[sid[i]];
+    const double o[3] = {x[nd], x[stride + nd], x[2 * stride + nd]};
+    double nrm[3], t, y[3];
+    surf_normal(s, o, nrm, t);
+    if (s.kind == 0) {
+      const double h = (o[0] - s.p[0]) * nrm[0] + (o[1] - s.p[1]) * nrm[1] + (o[2] - s.p[2]) * nrm[2];
+#pragma unroll
+      for (int k = 0; k < 3; k++) y[k] = o[k] - h * nrm[k];
+    } else if (s.kind == 1) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) y[k] = s.p[k] + s.R * nrm[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; k++) y[k] = (s.p[k] + t * s.u[k]) + s.R * nrm[k];
+    }
+    double dm = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      dm += (o[k] - y[k]) * (o[k] - y[k]);
+      x[k * stride + nd] = y[k];
+    }
+    v[0] = fmax(v[0], sqrt(dm));
+  }
+  grid_reduce<OpMax, 1, false>(v, 0ull, R, slot);
+}
+
+__global__ void __launch_bounds__(NT) k_surf_normals(const long long n, const int32_t* __restrict__ nodes,
+                                                     const int32_t* __restrict__ sid, const SurfaceDev* __restrict__ surfs,
+                                                     const double* __restrict__ x, double* __restrict__ out, const long long stride) {
+  const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+  if (i >= n) return;
+  const long long nd = nodes[i];
+  const double xx[3] = {x[nd], x[stride + nd], x[2 * stride + nd]};
+  double nrm[3], t;
+  surf_normal(surfs[sid[i]], xx, nrm, t);
+#pragma unroll
+  for (int k = 0; k < 3; k++) out[k * stride + nd] = nrm[k];
+}
+
+static void launch_surf_project(cudaStream_t st, long long n, const int32_t* nodes, const int32_t* sid, const SurfaceDev* surfs,
+                                const double* x, double* g, long long stride) {
+  if (n > 0) k_surf_project<<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>(n, nodes, sid, surfs, x, g, stride);
+}
+static void launch_surf_snap(cudaStream_t st, long long n, const int32_t* nodes, const int32_t* sid, const SurfaceDev* surfs,
+                             double* x, long long stride, const Reduce& R, int slot) {
+  long long nb = (n + NT - 1) / NT;
+  if (nb < 1) nb = 1;
+  if (nb > R.max_blocks) nb = R.max_blocks;
+  k_surf_snap<<<(unsigned)nb, NT, 0, st>>>(n, nodes, sid, surfs, x, stride, R, slot);
+}
+static void launch_surf_normals(cudaStream_t st, long long n, const int32_t* nodes, const int32_t* sid, const SurfaceDev* surfs,
+                                const double* x, double* out, long long stride) {
+  if (n > 0) k_surf_normals<<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>(n, nodes, sid, surfs, x, out, stride);
+}
+
 static void launch_elem_fixed_bits(cudaStream_t st, const MeshDev& m, const uint8_t* fixed, uint8_t* bits) {
   if (m.kind == KIND_SGRID)
     k_elem_fixed_bits<FL_SGRID><<<elem_grid<FL_SGRID>(m), NT, 0, st>>>(m, fixed, bits);
@@ -1774,7 +1876,7 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,
                                       launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_shared_sum,
-                                      launch_refine_sgrid};
+                                      launch_refine_sgrid, launch_surf_project, launch_surf_snap, launch_surf_normals};
 
 const Launchers* launchers() { return &g_launchers; }
 void set_variant(int metric_corners, int grad_corners) {

@@ -69,6 +69,13 @@ constexpr int BRICK_GTAB_BYTES = 16 + 8 * BRICK_MAX_NODES + 16 * BRICK_MAX_NODES
 constexpr int BRICK_EX_STRIDE = 25;
 constexpr int BRICK_EX_ZERO = BRICK_ELEMS * BRICK_EX_STRIDE;
 
+// analytic stand-in for a MeshGeometry evaluator: 0 plane (p, unit normal u), 1 sphere (centre p, R),
+// 2 cylinder (axis point p, unit axis u, R)
+struct SurfaceDev {
+  int kind;
+  double p[3], u[3], R;
+};
+
 struct Launchers {
   // metric of (x + alpha*s on unfixed nodes) vs reference w; result: out_d[slot] = sum, out_u[slot] = #invalid.
   // s may be null (alpha = 0).  elem_metric/elem_flag optional.
@@ -131,6 +138,16 @@ struct Launchers {
   // src + src_off, component stride src_stride) onto the (2ni-1) x (2nj-1) x (2nk-1) block at dst + dst_off
   void (*refine_sgrid)(cudaStream_t, int ni, int nj, int nk, const double* src, long long src_off, long long src_stride,
                        double* dst, long long dst_off, long long dst_stride);
+  // surface smoothing hooks over the list of non-fixed surface nodes (node id, surface id):
+  //   project: g -= (g.n) n with n = surface normal at x (get_gradient_2 / project_delta_to_tangent_plane)
+  //   snap:    x <- closest point of the surface; out_d[slot] = max displacement (snap_nodes)
+  //   normals: out <- n, component stride `stride` (get_surface_normals)
+  void (*surf_project)(cudaStream_t, long long n, const int32_t* nodes, const int32_t* sid, const SurfaceDev* surfs,
+                       const double* x, double* g, long long stride);
+  void (*surf_snap)(cudaStream_t, long long n, const int32_t* nodes, const int32_t* sid, const SurfaceDev* surfs, double* x,
+                    long long stride, const Reduce&, int slot);
+  void (*surf_normals)(cudaStream_t, long long n, const int32_t* nodes, const int32_t* sid, const SurfaceDev* surfs,
+                       const double* x, double* out, long long stride);
 };
 
 }  // namespace pmsk

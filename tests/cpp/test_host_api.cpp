@@ -148,6 +148,79 @@ int main() {
     EXPECT_EQ(line.find("WholeExtent=\"0 6 0 6 0 6\"") != std::string::npos, true);
     for (const char* f : {"cube.0.vts", "cube_init.pvd", "cube_init.0.vts", "cube_ref.pvd", "cube_ref.0.vts", "smootherlogcube_ref.txt"}) std::remove(f);
   }
+  {  // STKMesh + MeshGeometry with smooth_surfaces: hex8 box whose top face is a cylinder patch; face-interior nodes
+     // are MS_SURFACE (slide on their surface), box edges MS_CURVE and corners MS_VERTEX stay put (MeshSmoother.cpp:293-340)
+    const unsigned ne = 6, nn = ne + 1;
+    const size_t N = (size_t)nn * nn * nn;
+    std::vector<double> w(3 * N), x(3 * N);
+    std::vector<int8_t> dof(N);
+    std::vector<int32_t> ev(N, -1);
+    auto ztop = [](double xx) { return -2.0 + std::sqrt(9.0 - (xx - 0.5) * (xx - 0.5)); };
+    std::srand(7);
+    for (unsigned k = 0; k < nn; k++)
+      for (unsigned j = 0; j < nn; j++)
+        for (unsigned i = 0; i < nn; i++) {
+          const size_t n = i + (size_t)nn * (j + (size_t)nn * k);
+          const double X = (double)i / ne, Y = (double)j / ne, Z = (double)k / ne * ztop(X);
+          w[n] = X, w[N + n] = Y, w[2 * N + n] = Z;
+          const int nb = (i == 0 || i == ne) + (j == 0 || j == ne) + (k == 0 || k == ne);
+          dof[n] = nb == 3 ? 0 : nb == 2 ? 1 : nb == 1 ? 2 : 3;
+          if (nb == 1) ev[n] = i == 0 ? 0 : i == ne ? 1 : j == 0 ? 2 : j == ne ? 3 : k == 0 ? 4 : 5;
+          for (int d = 0; d < 3; d++)
+            x[d * N + n] = w[d * N + n] + (nb <= 1 ? 0.2 / ne * ((double)std::rand() / RAND_MAX - 0.5) : 0.0);
+        }
+    std::vector<int32_t> conn;
+    for (unsigned k = 0; k < ne; k++)
+      for (unsigned j = 0; j < ne; j++)
+        for (unsigned i = 0; i < ne; i++) {
+          auto id = [&](unsigned a, unsigned b, unsigned c) { return (int32_t)((i + a) + nn * ((j + b) + nn * (k + c))); };
+          for (int32_t v : {id(0, 0, 0), id(1, 0, 0), id(1, 1, 0), id(0, 1, 0), id(0, 0, 1), id(1, 0, 1), id(1, 1, 1), id(0, 1, 1)}) conn.push_back(v);
+        }
+    MeshGeometry geom;
+    geom.add_plane({{0, 0, 0}}, {{-1, 0, 0}});
+    geom.add_plane({{1, 0, 0}}, {{1, 0, 0}});
+    geom.add_plane({{0, 0, 0}}, {{0, -1, 0}});
+    geom.add_plane({{0, 1, 0}}, {{0, 1, 0}});
+    geom.add_plane({{0, 0, 0}}, {{0, 0, -1}});
+    geom.add_cylinder({{0.5, 0, -2}}, {{0, 1, 0}}, 3.0);
+    geom.set_classification(dof, ev);
+    PerceptMesh eMesh(3u);
+    eMesh.set_unstructured_mesh(PMS_HEX8, N, conn.size() / 8, conn.data());
+    eMesh.add_coordinate_state_fields();
+    eMesh.set_smooth_surfaces(true);
+    eMesh.set_field("coordinates_NM1", w.data());
+    eMesh.set_field("coordinates", x.data());
+    eMesh.setProperty("in_filename", "curved_box");
+    ReferenceMeshSmootherConjugateGradientImpl<STKMesh> sm(&eMesh, NULL, NULL, &geom, 15, 1.e-6, 1);
+    EXPECT_EQ(sm.get_fixed_flag((size_t)0).second, (int)MS_VERTEX);
+    EXPECT_EQ(sm.get_fixed_flag((size_t)(nn / 2)).second, (int)MS_CURVE);
+    EXPECT_EQ(sm.get_fixed_flag((size_t)(nn / 2 + nn * (nn / 2))).first, false);  // bottom-face interior: MS_SURFACE, free
+    EXPECT_EQ(sm.get_fixed_flag((size_t)(nn / 2 + nn * (nn / 2))).second, (int)MS_SURFACE);
+    sm.snap_nodes();  // the perturbed start goes onto the geometry (Refiner::snapAndSmooth snaps before smoothing)
+    eMesh.copy_field("coordinates_N", "coordinates");
+    sm.m_stage = 1;
+    bool valid = true;
+    const Double m0 = sm.total_metric(0.0, 1.0, valid);
+    sm.run();
+    EXPECT_EQ(sm.m_num_invalid, (size_t)0);
+    EXPECT_EQ(sm.m_global_metric < m0, true);
+    eMesh.get_field("coordinates", x.data());
+    double off_surface = 0, moved_fixed = 0;
+    for (size_t n = 0; n < N; n++) {
+      if (dof[n] < 2)
+        for (int d = 0; d < 3; d++) moved_fixed = std::fmax(moved_fixed, std::fabs(x[d * N + n] - w[d * N + n]));
+      if (ev[n] == 4) off_surface = std::fmax(off_surface, std::fabs(x[2 * N + n]));
+      if (ev[n] == 5) off_surface = std::fmax(off_surface, std::fabs(std::hypot(x[n] - 0.5, x[2 * N + n] + 2.0) - 3.0));
+    }
+    EXPECT_NEAR(off_surface, 0.0, 4e-15);
+    EXPECT_EQ(moved_fixed, 0.0);
+    sm.get_surface_normals(&eMesh);
+    const size_t top = nn / 2 + nn * (nn / 2 + (size_t)nn * ne);  // a node of the cylinder patch: unit radial normal
+    EXPECT_NEAR(std::hypot(sm.m_surface_normals[top], sm.m_surface_normals[2 * N + top]), 1.0, 1e-15);
+    std::printf("smooth_surfaces: metric %.6e -> %.6e, surface nodes within %.1e of the geometry\n", (double)m0,
+                (double)sm.m_global_metric, off_surface);
+    std::remove("smootherlogcurved_box.txt");
+  }
   {  // error convention: failures surface as std::runtime_error
     bool threw = false;
     try {
