@@ -130,6 +130,12 @@ int pms_get_edge_lengths(pms_ctx* ctx);
 /* total_metric(alpha) (Def.hpp:330-388): metric of coordinates + alpha*cg_s on
  * unfixed nodes; "coordinates" is left unchanged.  n_invalid may be NULL.       */
 int pms_total_metric(pms_ctx* ctx, int stage, double alpha, double* mtot, size_t* n_invalid);
+/* total_metric at several step lengths of the same direction in one pass (hex meshes: the per-corner Jacobian
+ * determinant and |A W^-1|^2 are polynomials in alpha, so extra alphas cost ~1/5 of a pass each).  Values agree with
+ * pms_total_metric to rounding (<= 1e-12 relative); the line-search driver uses it to evaluate the known backtracking
+ * sequence alpha, alpha/2, alpha/4, ... speculatively (option "speculate_line_search", default 1).                  */
+int pms_total_metric_multi(pms_ctx* ctx, int stage, int nalpha, const double* alphas, double* mtot, size_t* n_invalid);
+
 /* get_gradient (Def.hpp:1481-1520; gradient_functors.hpp:245-487): fills cg_g
  * (and cg_r = cg_g for unstructured meshes), zero at fixed nodes.               */
 int pms_get_gradient(pms_ctx* ctx, int stage);

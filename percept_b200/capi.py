@@ -89,6 +89,7 @@ class Api:
     }
     # product-only entry points (absent from the oracle twin)
     _SIGS_PRODUCT = {
+        "total_metric_multi": [C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_size_t)],
         "field_device_ptr": [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
         "comm_init": [C.c_void_p, C.c_int, C.c_int],
         "set_halo": [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -314,6 +315,14 @@ class Ctx:
         m, n = C.c_double(), C.c_size_t()
         self._call("total_metric", int(stage), float(alpha), C.byref(m), C.byref(n))
         return m.value, n.value
+
+    def total_metric_multi(self, stage, alphas):
+        """metric and invalid-element count at every alpha of `alphas` (product only)."""
+        a = np.ascontiguousarray(alphas, dtype=np.float64)
+        m = np.zeros(a.size)
+        n = (C.c_size_t * a.size)()
+        self._call("total_metric_multi", int(stage), int(a.size), _dptr(a), _dptr(m), n)
+        return m, np.array(list(n), dtype=np.int64)
 
     def get_gradient(self, stage):
         self._call("get_gradient", int(stage))

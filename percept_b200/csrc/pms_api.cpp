@@ -287,9 +287,47 @@ void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t
   if (ninv) *ninv = n;
   (void)count_eval;
   if (c->cache_metric) {
-    if (c->cache.size() >= 8) c->cache.erase(c->cache.begin());
+    if (c->cache.size() >= pms_ctx::CACHE_CAP) c->cache.erase(c->cache.begin());
     c->cache.push_back({X.version, S.version, W.version, stage, alpha, m, n, c->use_ref_mesh});
   }
+}
+
+// total_metric at MULTI_ALPHA_NB step lengths in one pass (hex meshes, one block).  Returns false when the kernel is
+// not available for this mesh / build; the caller then evaluates one alpha at a time.
+bool op_total_metric_multi(pms_ctx* c, int stage, const double* alphas, double* mtot, uint64_t* ninv) {
+  constexpr int NB = pmsk::MULTI_ALPHA_NB;
+  if (c->dev_blocks.size() != 1 || c->keep_elem || c->strict_fp) return false;
+  DField& X = c->field("coordinates");
+  DField& S = c->field("cg_s");
+  DField& W = c->field("coordinates_NM1");
+  {
+    Timed t(c, FAM_METRIC);
+    if (!c->L->metric_multi(c->stream, c->dev_blocks[0], stage, c->use_ref_mesh ? 1 : 0, X.d, S.d, W.d, c->Npad, alphas, c->R, 0)) {
+      c->launches--;
+      c->fam_launches[FAM_METRIC]--;
+      return false;
+    }
+    check_launch(c, "metric_multi");
+  }
+  fetch(c, 0, 2 * NB, 0);
+  double v[2 * NB];
+  for (int k = 0; k < 2 * NB; k++) v[k] = c->h_out_d[k];
+  allreduce(c, v, 2 * NB, NCCL_SUM);
+  for (int k = 0; k < NB; k++) {
+    mtot[k] = v[k];
+    ninv[k] = (uint64_t)v[NB + k];
+  }
+  if (c->cache_metric)
+    for (int k = 0; k < NB; k++) {
+      bool have = false;
+      for (auto& e : c->cache)
+        have = have || (e.xv == X.version && e.wv == W.version && e.sv == S.version && e.stage == stage && e.alpha == alphas[k] &&
+                        e.use_ref == c->use_ref_mesh);
+      if (have) continue;
+      if (c->cache.size() >= pms_ctx::CACHE_CAP) c->cache.erase(c->cache.begin());
+      c->cache.push_back({X.version, S.version, W.version, stage, alphas[k], mtot[k], ninv[k], c->use_ref_mesh});
+    }
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -772,6 +810,27 @@ struct Driver {
     return m;
   }
 
+  // Line-search speculation: the backtracking trials are alpha, alpha*tau, alpha*tau^2, ... (and the quadratic fit's
+  // a1 = alpha/2 continues the same sequence), known before their outcomes.  One multi-alpha pass evaluates the next
+  // MULTI_ALPHA_NB of them into the metric cache; tm() then finds them there.  Same decisions, fewer passes.
+  void speculate(double alpha, double tau) {
+    if (!c->speculate_line_search || !c->cache_metric || c->keep_elem) return;
+    {
+      const uint64_t xv = c->field("coordinates").version, sv = c->field("cg_s").version, wv = c->field("coordinates_NM1").version;
+      for (auto& e : c->cache)
+        if (e.xv == xv && e.wv == wv && e.sv == sv && e.stage == st->stage && e.alpha == alpha && e.use_ref == c->use_ref_mesh) return;
+    }
+    constexpr int NB = pmsk::MULTI_ALPHA_NB;
+    double al[NB], m[NB];
+    uint64_t n[NB];
+    double a = alpha;
+    for (int k = 0; k < NB; k++) {
+      al[k] = a;
+      a *= tau;  // the very multiplication the loop below performs, so the cache keys match bit for bit
+    }
+    if (op_total_metric_multi(c, st->stage, al, m, n)) st->n_metric_evals++;
+  }
+
   void s_equals_r() {  // copy_field(cg_s, cg_r)
     op_copy(c, "cg_s", "cg_r");
     halo_exchange(c, "cg_s");
@@ -801,6 +860,7 @@ struct Driver {
     int liter = 0;
     const int niter = 1000;
     while (!converged && liter < niter) {
+      speculate(alpha, tau);
       metric = tm(alpha, total_valid, &n_invalid);
       const double mfac = alpha * armijo_offset_factor * 1.0;
       converged = (metric < metric_0 + mfac);
@@ -822,6 +882,7 @@ struct Driver {
     }
     liter = 0;
     while (!converged && liter < niter) {
+      speculate(alpha, tau);
       metric = tm(alpha, total_valid);
       const double mfac = alpha * armijo_offset_factor;
       converged = (metric < metric_0 + mfac);
@@ -1081,6 +1142,8 @@ int pms_set_option(pms_ctx* c, const char* key, double v) {
       c->d_elem_metric = dalloc<double>(c->Epad);
       c->d_elem_flag = dalloc<int32_t>(c->Epad);
     }
+  } else if (k == "speculate_line_search") {
+    c->speculate_line_search = v != 0;
   } else if (k == "smooth_surfaces") {  // PerceptMesh::get_smooth_surfaces (mesh_adapt --smooth_surfaces)
     c->smooth_surfaces = v != 0;
     if (c->committed) apply_classification(c);
@@ -1441,7 +1504,7 @@ int pms_commit(pms_ctx* c) {
     maxb = std::max(maxb, nb + 8);
   }
   c->R.max_blocks = (int)maxb;
-  c->R.partial_d = dalloc<double>((size_t)3 * maxb);
+  c->R.partial_d = dalloc<double>((size_t)pmsk::REDUCE_MAX_NV * maxb);
   c->R.partial_u = dalloc<unsigned long long>((size_t)maxb);
   c->R.ticket = dalloc<unsigned int>(1);
   PMS_CUDA(cudaMemset(c->R.ticket, 0, sizeof(unsigned int)));
@@ -1779,6 +1842,26 @@ int pms_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, size_t* 
   uint64_t n;
   op_total_metric(c, stage, alpha, mtot, &n);
   if (n_invalid) *n_invalid = (size_t)n;
+  PMS_CATCH
+}
+
+int pms_total_metric_multi(pms_ctx* c, int stage, int nalpha, const double* alphas, double* mtot, size_t* n_invalid) {
+  PMS_TRY
+  require_committed(c);
+  if (nalpha < 1 || !alphas || !mtot) throw PmsError(PMS_ERR_ARG, "bad multi-alpha request");
+  constexpr int NB = pmsk::MULTI_ALPHA_NB;
+  for (int k0 = 0; k0 < nalpha; k0 += NB) {
+    double al[NB], m[NB];
+    uint64_t n[NB];
+    const int cnt = std::min(NB, nalpha - k0);
+    for (int k = 0; k < NB; k++) al[k] = alphas[k0 + std::min(k, cnt - 1)];
+    if (!op_total_metric_multi(c, stage, al, m, n))  // tet4 / strict build / multi-block: one pass per alpha
+      for (int k = 0; k < cnt; k++) op_total_metric(c, stage, al[k], &m[k], &n[k]);
+    for (int k = 0; k < cnt; k++) {
+      mtot[k0 + k] = m[k];
+      if (n_invalid) n_invalid[k0 + k] = (size_t)n[k];
+    }
+  }
   PMS_CATCH
 }
 

@@ -110,6 +110,8 @@ struct pms_ctx {
     bool use_ref;
   };
   std::vector<CacheEnt> cache;
+  static constexpr size_t CACHE_CAP = 32;
+  bool speculate_line_search = true;  // evaluate the line search's alpha_init * tau^k trials in multi-alpha passes
   bool adj_fixed = false;
 
   // multi-GPU

@@ -177,6 +177,78 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
   return val0 + val1;
 }
 
+// Hex metric at NB trial step lengths in one pass (line search).  With x(alpha) = x + alpha*s every corner edge is
+// a + alpha*b, so per corner   det A(alpha) = d0 + d1 alpha + d2 alpha^2 + d3 alpha^3   (triple-product expansion) and
+// T'(alpha) = A(alpha) cof(W)^T = Tx + alpha Ts, hence   y(alpha) = |T'|^2 = y0 + 2 y1 alpha + y2 alpha^2.
+// The 8 coefficients cost about two single evaluations of the corner; each further alpha costs ~20 FP64 instructions
+// (two Horner forms, one rsqrt) instead of ~94.  vs must already be zero at fixed nodes (update_coordinates.cpp:255).
+// sum[k] += metric of this element at al[k]; bit k of invmask set when any corner has det A(al[k]) <= 0.
+template <int STAGE, int NB, class VC, class VS, class VO>
+PMS_DI void hex_metric_multi(const VC& vc, const VS& vs, const VO& vo, const double (&al)[NB], double (&sum)[NB], unsigned& invmask) {
+  invmask = 0;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    double a0[3], a1[3], a2[3], b0[3], b1[3], b2[3], w0[3], w1[3], w2[3];
+    corner_edge<0>(vc, c, a0);
+    corner_edge<1>(vc, c, a1);
+    corner_edge<2>(vc, c, a2);
+    corner_edge<0>(vs, c, b0);
+    corner_edge<1>(vs, c, b1);
+    corner_edge<2>(vs, c, b2);
+    corner_edge<0>(vo, c, w0);
+    corner_edge<1>(vo, c, w1);
+    corner_edge<2>(vo, c, w2);
+    double K0[3], L[3], L2[3], M[3], C0[3];
+    cross3(a1, a2, K0);
+    cross3(a1, b2, L);
+    cross3(b1, a2, L2);
+    cross3(b1, b2, M);
+#pragma unroll
+    for (int r = 0; r < 3; r++) L[r] += L2[r];
+    const double d0 = dot3(a0, K0), d1 = dot3(a0, L) + dot3(b0, K0), d2 = dot3(a0, M) + dot3(b0, L), d3 = dot3(b0, M);
+    cross3(w1, w2, C0);
+    const double detW = dot3(w0, C0);
+    if (STAGE == 0) {
+      const double bw = BETA_MULT * detW;
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+        const double detA = fma(al[k], fma(al[k], fma(al[k], d3, d2), d1), d0);
+        const double vv = bw - detA;
+        const double vp = vv > 0.0 ? vv : 0.0;
+        sum[k] += vp * vp;
+        if (!(detA > 0.0)) invmask |= 1u << k;
+      }
+    } else {
+      double C1[3], C2[3];
+      cross3(w2, w0, C1);
+      cross3(w0, w1, C2);
+      double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const double tx = a0[r] * C0[q] + a1[r] * C1[q] + a2[r] * C2[q];
+          const double ts = b0[r] * C0[q] + b1[r] * C1[q] + b2[r] * C2[q];
+          y0 += tx * tx;
+          y1 += tx * ts;
+          y2 += ts * ts;
+        }
+      const double y1x2 = 2.0 * y1, cw = FAC_3SQRT3 * fabs(detW);
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+        const double y = fma(al[k], fma(al[k], y2, y1x2), y0);
+        const double detA = fma(al[k], fma(al[k], fma(al[k], d3, d2), d1), d0);
+        const bool ok = detA > 0.0;
+        const double P = cw * detA;
+        const double rr = fast_rsqrt(ok ? y * P * P : 1.0);
+        const double yr = y * rr;
+        sum[k] += ok ? y * yr - detW : 0.0;
+        if (!ok) invmask |= 1u << k;
+      }
+    }
+  }
+}
+
 template <int STAGE, bool GRAD>
 PMS_DI double hex_metric_fast(const double (&vc)[8][3], const double (&vo)[8][3], bool& valid, double (&grad)[8][3]) {
   return hex_metric_fast_v<STAGE, GRAD>(RegVerts(vc), RegVerts(vo), valid, grad);

@@ -1075,6 +1075,200 @@ static bool launch_grad_bricks(cudaStream_t st, const MeshDev& m, const BrickDev
 }
 
 // ------------------------------------------------------------------------------------------------
+// Occupancy-oriented hex metric (metric variant 4).  k_elem_pipe hides memory latency by software pipelining at
+// 2 warps per scheduler and keeps all 48 vertex doubles in registers (~250).  Here the vertices stay in the thread's
+// shared-memory column and are read in place (immediate-offset LDS), x + alpha*s is formed in place, and the register
+// budget is capped so that OCC_MINB CTAs (OCC_MINB warps per scheduler) are resident: latency is hidden by other CTAs
+// instead of by a prefetch, and the FP64 pipe sees more independent instruction streams.
+// ------------------------------------------------------------------------------------------------
+#ifndef OCC_MINB
+#define OCC_MINB 3
+#endif
+template <int FL, int STAGE, bool WITH_S>
+__global__ void __launch_bounds__(NTP, OCC_MINB) k_metric_occ(const MeshDev m, const double* __restrict__ x, const double* __restrict__ s,
+                                                              const double* __restrict__ w, const long long stride,
+                                                              const double alpha, const Reduce R, const int slot) {
+  constexpr int NVAL = 8 * 3 * (WITH_S ? 3 : 2);
+  extern __shared__ double sm[];  // [NVAL][NTP]
+  const int tid = threadIdx.x;
+  auto slot_in = [&](int arr, int a, int r) -> double* { return sm + ((arr * 8 + a) * 3 + r) * NTP + tid; };
+  double val[1] = {0.0};
+  unsigned long long inv = 0;
+  const long long ntiles = num_ptiles<FL>(m);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long e, n0;
+    if (!ptile_element<FL>(m, tile, e, n0)) continue;
+    const long long sj = m.ni, sk = (long long)m.ni * m.nj;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      long long nid;
+      if (FL == FL_SGRID)
+        nid = n0 + (a & 1) + ((a >> 1) & 1) * sj + (a >> 2) * sk;
+      else
+        nid = __ldg(&m.conn[(long long)a * m.conn_stride + e]);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        cp_async8(slot_in(0, a, r), &x[r * stride + nid]);
+        cp_async8(slot_in(1, a, r), &w[r * stride + nid]);
+        if (WITH_S) cp_async8(slot_in(2, a, r), &s[r * stride + nid]);
+      }
+    }
+    unsigned bits = 0;
+    if (WITH_S) bits = m.elem_fixed_bits[m.elem_off + e];
+    cp_async_commit();
+    cp_async_wait_all();
+    if (WITH_S) {
+#pragma unroll
+      for (int a = 0; a < 8; a++)
+        if (!((bits >> a) & 1u)) {
+#pragma unroll
+          for (int r = 0; r < 3; r++) *slot_in(0, a, r) += alpha * *slot_in(2, a, r);  // update_coordinates.cpp:255-256
+        }
+    }
+    const SmemVerts<FL == FL_HEX8, NTP> VC(slot_in(0, 0, 0)), VO(slot_in(1, 0, 0));
+    bool valid;
+    double grad[8][3];
+    const double mm = hex_metric_fast_v<STAGE, false>(VC, VO, valid, grad);
+    bool counted = true;
+    if (FL != FL_SGRID && m.elem_owned) counted = m.elem_owned[e] != 0;
+    if (counted) {
+      val[0] += mm;
+      inv += valid ? 0 : 1;
+    }
+  }
+  grid_reduce<OpSum, 1, true>(val, inv, R, slot);
+}
+
+template <int FL, int STAGE, bool WITH_S>
+static void launch_metric_occ(cudaStream_t st, const MeshDev& m, const double* x, const double* s, const double* w, long long stride,
+                              double alpha, const Reduce& R, int slot) {
+  const size_t smem = (size_t)8 * 3 * (WITH_S ? 3 : 2) * NTP * sizeof(double);
+  auto kern = k_metric_occ<FL, STAGE, WITH_S>;
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NTP, smem);
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  const long long nt = num_ptiles<FL>(m);
+  const long long cap = 148LL * blocks_per_sm;
+  kern<<<(unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), NTP, smem, st>>>(m, x, s, w, stride, alpha, R, slot);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-alpha hex metric: the line search's trial sequence alpha_init * tau^k is known before its outcomes are, so one
+// pass evaluates NB of them (hex_metric_multi: per-corner polynomial coefficients once, ~20 FP64 per extra alpha).
+// Vertices of x, s, w stay in the thread's shared-memory column (in place, single buffer, 2 CTAs/SM interleave).
+// ------------------------------------------------------------------------------------------------
+template <int NB>
+struct AlphaPack {
+  double a[NB];
+};
+template <int FL, int STAGE, int NB>
+__global__ void __launch_bounds__(NTP, 2) k_metric_multi(const MeshDev m, const double* __restrict__ x, const double* __restrict__ s,
+                                                         const double* __restrict__ w, const long long stride,
+                                                         const AlphaPack<NB> al, const Reduce R, const int slot) {
+  extern __shared__ double sm[];  // [72][NTP]
+  const int tid = threadIdx.x;
+  auto slot_in = [&](int arr, int a, int r) -> double* { return sm + ((arr * 8 + a) * 3 + r) * NTP + tid; };
+  double sums[NB];
+  unsigned cnt[NB];
+#pragma unroll
+  for (int k = 0; k < NB; k++) {
+    sums[k] = 0.0;
+    cnt[k] = 0;
+  }
+  const long long ntiles = num_ptiles<FL>(m);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long e, n0;
+    if (!ptile_element<FL>(m, tile, e, n0)) continue;
+    const long long sj = m.ni, sk = (long long)m.ni * m.nj;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      long long nid;
+      if (FL == FL_SGRID)
+        nid = n0 + (a & 1) + ((a >> 1) & 1) * sj + (a >> 2) * sk;
+      else
+        nid = __ldg(&m.conn[(long long)a * m.conn_stride + e]);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        cp_async8(slot_in(0, a, r), &x[r * stride + nid]);
+        cp_async8(slot_in(1, a, r), &w[r * stride + nid]);
+        cp_async8(slot_in(2, a, r), &s[r * stride + nid]);
+      }
+    }
+    const unsigned bits = m.elem_fixed_bits[m.elem_off + e];
+    cp_async_commit();
+    cp_async_wait_all();
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+      if ((bits >> a) & 1u) {  // fixed nodes do not move (update_coordinates.cpp:255-256)
+#pragma unroll
+        for (int r = 0; r < 3; r++) *slot_in(2, a, r) = 0.0;
+      }
+    const SmemVerts<FL == FL_HEX8, NTP> VC(slot_in(0, 0, 0)), VO(slot_in(1, 0, 0)), VS(slot_in(2, 0, 0));
+    bool counted = true;
+    if (FL != FL_SGRID && m.elem_owned) counted = m.elem_owned[e] != 0;
+    double es[NB];
+#pragma unroll
+    for (int k = 0; k < NB; k++) es[k] = 0.0;
+    unsigned invmask;
+    hex_metric_multi<STAGE, NB>(VC, VS, VO, al.a, es, invmask);
+    if (counted) {
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+        sums[k] += es[k];
+        cnt[k] += (invmask >> k) & 1u;
+      }
+    }
+  }
+  double v[2 * NB];
+#pragma unroll
+  for (int k = 0; k < NB; k++) {
+    v[k] = sums[k];
+    v[NB + k] = (double)cnt[k];
+  }
+  grid_reduce<OpSum, 2 * NB, false>(v, 0ull, R, slot);
+}
+
+template <int FL, int STAGE>
+static void launch_metric_multi2(cudaStream_t st, const MeshDev& m, const double* x, const double* s, const double* w, long long stride,
+                                 const double* alphas, const Reduce& R, int slot) {
+  constexpr int NB = MULTI_ALPHA_NB;
+  static_assert(2 * NB <= REDUCE_MAX_NV, "reduction scratch too small");
+  const size_t smem = (size_t)72 * NTP * sizeof(double);
+  auto kern = k_metric_multi<FL, STAGE, NB>;
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NTP, smem);
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  AlphaPack<NB> al;
+  for (int k = 0; k < NB; k++) al.a[k] = alphas[k];
+  const long long nt = num_ptiles<FL>(m);
+  long long cap = 148LL * blocks_per_sm;
+  if (cap > R.max_blocks) cap = R.max_blocks;
+  kern<<<(unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), NTP, smem, st>>>(m, x, s, w, stride, al, R, slot);
+}
+static bool launch_metric_multi(cudaStream_t st, const MeshDev& m, int stage, int use_ref, const double* x, const double* s,
+                                const double* w, long long stride, const double* alphas, const Reduce& R, int slot) {
+  if (STRICT || m.kind == KIND_TET4 || (stage != 0 && !use_ref)) return false;
+  if (m.kind == KIND_SGRID) {
+    if (stage == 0)
+      launch_metric_multi2<FL_SGRID, 0>(st, m, x, s, w, stride, alphas, R, slot);
+    else
+      launch_metric_multi2<FL_SGRID, 1>(st, m, x, s, w, stride, alphas, R, slot);
+  } else {
+    if (stage == 0)
+      launch_metric_multi2<FL_HEX8, 0>(st, m, x, s, w, stride, alphas, R, slot);
+    else
+      launch_metric_multi2<FL_HEX8, 1>(st, m, x, s, w, stride, alphas, R, slot);
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: total element metric at x + alpha*s          (total_element_metric.cpp:271-307, Def.hpp:330-388)
 // ------------------------------------------------------------------------------------------------
 template <int FL, int STAGE, bool USE_REF, bool WITH_S>
@@ -1132,7 +1326,15 @@ template <int FL, int STAGE, bool USE_REF>
 static void launch_metric2(cudaStream_t st, const MeshDev& m, const double* x, const double* s, const double* w,
                            long long stride, double alpha, const Reduce& R, int slot, double* em, int32_t* ef,
                            const uint8_t* fixed) {
-  if (!STRICT && g_metric_corners == 2) {
+  if (!STRICT && g_metric_corners == 4 && fast_hex<FL, STAGE, USE_REF>() && FL != FL_TET4 && !em && !ef) {
+    constexpr int F2 = FL == FL_TET4 ? FL_HEX8 : FL;
+    if (s && alpha != 0.0)
+      launch_metric_occ<F2, STAGE, true>(st, m, x, s, w, stride, alpha, R, slot);
+    else
+      launch_metric_occ<F2, STAGE, false>(st, m, x, s, w, stride, alpha, R, slot);
+    return;
+  }
+  if (!STRICT && (g_metric_corners == 2 || g_metric_corners == 4)) {
     if (s && alpha != 0.0)
       launch_elem_pipe<FL, STAGE, USE_REF, false, true>(st, m, x, s, w, stride, alpha, nullptr, 0, R, slot, em, ef);
     else
@@ -1876,7 +2078,7 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,
                                       launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_shared_sum,
-                                      launch_refine_sgrid, launch_surf_project, launch_surf_snap, launch_surf_normals};
+                                      launch_metric_multi, launch_refine_sgrid, launch_surf_project, launch_surf_snap, launch_surf_normals};
 
 const Launchers* launchers() { return &g_launchers; }
 void set_variant(int metric_corners, int grad_corners) {

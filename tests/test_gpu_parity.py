@@ -242,7 +242,7 @@ def test_metric_cache_does_not_change_results():
     nele = 8
     X, W = meshes.perturbed_coords(nele, 0.3)
     a = meshes.build(pb.api, "sgrid", nele, X, W, True, {"cache_metric": 0})
-    b = meshes.build(pb.api, "sgrid", nele, X, W, True, {"cache_metric": 1})
+    b = meshes.build(pb.api, "sgrid", nele, X, W, True, {"cache_metric": 1, "speculate_line_search": 0})  # exact re-use only
     sa = a.run_algorithm(6, 0.0)
     sb = b.run_algorithm(6, 0.0)
     assert np.array_equal(a.download("coordinates"), b.download("coordinates"))
@@ -283,7 +283,7 @@ def test_kernel_variants_agree_with_oracle(kind, variant):
     5 warp-specialised bricks) against the oracle."""
     for stage, eps in ((1, 0.25), (0, 1.0), (1, 1.0)):
         g, o = pair(kind, 11, eps, strict=0)
-        g.set_option("variant_metric_corners", variant if variant < 4 else 2)
+        g.set_option("variant_metric_corners", variant if variant < 4 else 4)  # 4 = occupancy-oriented in-place metric
         g.set_option("variant_grad_corners", variant)  # 4/5 = scratch-free brick gradient (hex8), needs keep_element_metrics off
         if variant >= 4:
             g.set_option("keep_element_metrics", 0)
@@ -383,6 +383,53 @@ def _isolated_hexes(n):
     W = np.concatenate([corner + np.array([2.0 * (e % 7), 2.0 * ((e // 7) % 7), 2.0 * (e // 49)]) for e in range(n)]).T.copy()
     conn = np.arange(8 * n, dtype=np.int32).reshape(n, 8)
     return np.ascontiguousarray(W), conn, np.zeros(8 * n, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("kind", ["sgrid", "hex8", "tet4"])
+@pytest.mark.parametrize("eps", [0.25, 1.0])
+def test_multi_alpha_metric_matches_single_evaluations_and_oracle(kind, eps):
+    """pms_total_metric_multi: per-corner polynomial-in-alpha evaluation (hex) of the line search's trial sequence; tet4
+    falls back to one pass per alpha.  Includes alpha = 0, negative and large steps that invert elements.
+    Tolerance: 1e-12 relative on the valid mesh (eps 0.25).  On the tangled mesh (eps 1.0; ShapeB1 there is outside the
+    algorithm's domain, corners with det A -> 0+ dominate the sum) the value is ill-conditioned: the reference's own
+    rounding of x + alpha*s already moves det A by ~eps*|x||cof A|, i.e. the total by ~1e-12 relative, so the
+    polynomial form is held to 2e-11 there while invalid-element counts stay exact."""
+    g, o = pair(kind, 9, eps, strict=0)
+    g.set_option("keep_element_metrics", 0)  # (the multi-alpha kernel does not write per-element values)
+    n = g.num_nodes_local
+    s = meshes.seeded_field(n, 3, 0.02 / 9)
+    g.upload("cg_s", s)
+    o.upload("cg_s", s)
+    alphas = [8.0 * 0.5 ** k for k in range(11)] + [0.0, -0.75, 0.3]
+    for stage in (0, 1):
+        before = g.launch_count()
+        mg, ng = g.total_metric_multi(stage, alphas)
+        assert g.launch_count() - before == (2 if kind != "tet4" else len(alphas))  # 14 alphas = 2 passes of 8
+        g.set_option("cache_metric", 0)
+        for k, a in enumerate(alphas):
+            mo, no = o.total_metric(stage, a)
+            ms, ns = g.total_metric(stage, a)
+            assert ng[k] == no == ns
+            tol = 1e-12 if eps < 1.0 or kind == "tet4" else 2e-11
+            assert abs(mg[k] - mo) <= tol * abs(mo) + 1e-300 and abs(ms - mo) <= 1e-12 * abs(mo) + 1e-300
+        g.set_option("cache_metric", 1)
+
+
+def test_line_search_speculation_does_not_change_the_run():
+    """speculate_line_search only changes how many passes evaluate the trial alphas, not the decisions."""
+    out = []
+    for spec in (0, 1):
+        g, _ = pair("hex8", 10, 1.0, strict=0)
+        g.set_option("keep_element_metrics", 0)
+        g.set_option("cache_metric", 1)
+        g.set_option("speculate_line_search", spec)
+        st = g.run_algorithm(6, 0.0)
+        out.append((st.stage, st.iter, st.num_invalid, st.n_line_search_halvings, st.global_metric, g.download("coordinates"), st.n_metric_evals))
+    a, b = out
+    assert a[:4] == b[:4]
+    assert abs(a[4] - b[4]) <= 1e-11 * abs(a[4])
+    assert np.abs(a[5] - b[5]).max() <= 1e-10
+    assert b[6] < a[6]  # fewer metric passes
 
 
 @pytest.mark.parametrize("mesh", ["fan", "isolated"])
