@@ -292,33 +292,32 @@ void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t
   }
 }
 
-// total_metric at MULTI_ALPHA_NB step lengths in one pass (hex meshes, one block).  Returns false when the kernel is
+// total_metric at nb (8 or 12) step lengths in one pass (hex meshes, one block).  Returns false when the kernel is
 // not available for this mesh / build; the caller then evaluates one alpha at a time.
-bool op_total_metric_multi(pms_ctx* c, int stage, const double* alphas, double* mtot, uint64_t* ninv) {
-  constexpr int NB = pmsk::MULTI_ALPHA_NB;
-  if (c->dev_blocks.size() != 1 || c->keep_elem || c->strict_fp) return false;
+bool op_total_metric_multi(pms_ctx* c, int stage, int nb, const double* alphas, double* mtot, uint64_t* ninv) {
+  if (c->dev_blocks.size() != 1 || c->keep_elem || c->strict_fp || nb > pmsk::MULTI_ALPHA_NB) return false;
   DField& X = c->field("coordinates");
   DField& S = c->field("cg_s");
   DField& W = c->field("coordinates_NM1");
   {
     Timed t(c, FAM_METRIC);
-    if (!c->L->metric_multi(c->stream, c->dev_blocks[0], stage, c->use_ref_mesh ? 1 : 0, X.d, S.d, W.d, c->Npad, alphas, c->R, 0)) {
+    if (!c->L->metric_multi(c->stream, c->dev_blocks[0], stage, c->use_ref_mesh ? 1 : 0, nb, X.d, S.d, W.d, c->Npad, alphas, c->R, 0)) {
       c->launches--;
       c->fam_launches[FAM_METRIC]--;
       return false;
     }
     check_launch(c, "metric_multi");
   }
-  fetch(c, 0, 2 * NB, 0);
-  double v[2 * NB];
-  for (int k = 0; k < 2 * NB; k++) v[k] = c->h_out_d[k];
-  allreduce(c, v, 2 * NB, NCCL_SUM);
-  for (int k = 0; k < NB; k++) {
+  fetch(c, 0, 2 * nb, 0);
+  double v[2 * pmsk::MULTI_ALPHA_NB];
+  for (int k = 0; k < 2 * nb; k++) v[k] = c->h_out_d[k];
+  allreduce(c, v, 2 * nb, NCCL_SUM);
+  for (int k = 0; k < nb; k++) {
     mtot[k] = v[k];
-    ninv[k] = (uint64_t)v[NB + k];
+    ninv[k] = (uint64_t)v[nb + k];
   }
   if (c->cache_metric)
-    for (int k = 0; k < NB; k++) {
+    for (int k = 0; k < nb; k++) {
       bool have = false;
       for (auto& e : c->cache)
         have = have || (e.xv == X.version && e.wv == W.version && e.sv == S.version && e.stage == stage && e.alpha == alphas[k] &&
@@ -820,15 +819,48 @@ struct Driver {
       for (auto& e : c->cache)
         if (e.xv == xv && e.wv == wv && e.sv == sv && e.stage == st->stage && e.alpha == alpha && e.use_ref == c->use_ref_mesh) return;
     }
-    constexpr int NB = pmsk::MULTI_ALPHA_NB;
-    double al[NB], m[NB];
-    uint64_t n[NB];
+    // batch size from the previous line search: it visited spec_prev trials of the sequence (+1 for the quadratic
+    // fit's a1); 8 when that is enough, else 12
+    constexpr int NBMAX = pmsk::MULTI_ALPHA_NB;
+    const int nb = (c->spec_prev + 1 <= 8 && c->spec_prev > 0) ? 8 : NBMAX;
+    double al[NBMAX], m[NBMAX];
+    uint64_t n[NBMAX];
     double a = alpha;
-    for (int k = 0; k < NB; k++) {
+    for (int k = 0; k < nb; k++) {
       al[k] = a;
       a *= tau;  // the very multiplication the loop below performs, so the cache keys match bit for bit
     }
-    if (op_total_metric_multi(c, st->stage, al, m, n)) st->n_metric_evals++;
+    if (op_total_metric_multi(c, st->stage, nb, al, m, n)) st->n_metric_evals++;
+  }
+  int spec_cur = 0;  // trials visited by the current line search (c->spec_prev: by the previous one)
+
+  // Pass fusion (with line-search speculation on): the fused metric+gradient kernel's metric is put in the metric cache
+  // as the alpha = 0 value at these coordinates, and a gradient computed at the end of the previous iteration is reused.
+  bool fuse_passes() const { return c->speculate_line_search && c->cache_metric && !c->keep_elem && c->use_ref_mesh && !c->strict_fp; }
+  void gradient_here() {
+    DField& X = c->field("coordinates");
+    DField& W = c->field("coordinates_NM1");
+    if (c->pre_valid && c->pre_xv == X.version && c->pre_wv == W.version && c->pre_gv == c->field("cg_g").version &&
+        c->pre_stage == st->stage && fuse_passes()) {
+      c->pre_valid = false;
+      return;  // cg_g already holds f'(x) for these coordinates
+    }
+    c->pre_valid = false;
+    double m;
+    uint64_t n;
+    op_gradient(c, st->stage, &m, &n, /*write_r=*/false);  // cg_r = cg_g (Def.hpp:1508) is overwritten by r = -g
+    st->n_gradient_evals++;
+    // (a metric of exactly 0 is the reference's early-exit test `metric_check == 0.0`, Def.hpp:1041: at that noise floor the
+    //  metric kernel's own value decides, as without fusion)
+    if (fuse_passes() && m != 0.0) {
+      bool have = false;
+      for (auto& e : c->cache)
+        have = have || (e.xv == X.version && e.wv == W.version && e.stage == st->stage && e.alpha == 0.0 && e.use_ref == c->use_ref_mesh);
+      if (!have) {
+        if (c->cache.size() >= pms_ctx::CACHE_CAP) c->cache.erase(c->cache.begin());
+        c->cache.push_back({X.version, c->field("cg_s").version, W.version, st->stage, 0.0, m, n, c->use_ref_mesh});
+      }
+    }
   }
 
   void s_equals_r() {  // copy_field(cg_s, cg_r)
@@ -859,8 +891,10 @@ struct Driver {
     total_valid = false;
     int liter = 0;
     const int niter = 1000;
+    spec_cur = 0;
     while (!converged && liter < niter) {
       speculate(alpha, tau);
+      spec_cur++;
       metric = tm(alpha, total_valid, &n_invalid);
       const double mfac = alpha * armijo_offset_factor * 1.0;
       converged = (metric < metric_0 + mfac);
@@ -883,6 +917,7 @@ struct Driver {
     liter = 0;
     while (!converged && liter < niter) {
       speculate(alpha, tau);
+      spec_cur++;
       metric = tm(alpha, total_valid);
       const double mfac = alpha * armijo_offset_factor;
       converged = (metric < metric_0 + mfac);
@@ -898,6 +933,7 @@ struct Driver {
       ++liter;
     }
     if (!converged) throw PmsError(PMS_ERR_SMOOTHER, "can't reduce metric");
+    c->spec_prev = spec_cur;
     const double a1 = alpha / 2., a2 = alpha;
     const double f0 = metric_0, f1 = tm(a1, total_valid), f2 = tm(a2, total_valid);
     const double den = 2. * (a2 * (-f0 + f1) + a1 * (f0 - f2));
@@ -927,12 +963,7 @@ struct Driver {
       }
     }
     // f'(x) (+ the metric at the same x from the same pass, which is what metric_check evaluates)
-    {
-      double m;
-      uint64_t n;
-      op_gradient(c, st->stage, &m, &n, /*write_r=*/false);  // cg_r = cg_g (Def.hpp:1508) is overwritten by r = -g below
-      st->n_gradient_evals++;
-    }
+    gradient_here();
     // r = -g ; dold = d.d ; dmid = r.d ; dnew = r.r   (Def.hpp:1034-1037)
     {
       DField& G = c->field("cg_g");
@@ -988,6 +1019,17 @@ struct Driver {
         tm(0.0, total_valid_0);
         if (!total_valid_0) throw PmsError(PMS_ERR_SMOOTHER, "bad mesh after snap_node_positions...");
       }
+    }
+    if (fuse_passes()) {
+      // the metric at the new coordinates comes from the fused metric+gradient pass whose gradient the next
+      // iteration starts with (same x): one pass instead of a metric pass now and a gradient pass then
+      c->pre_valid = false;
+      gradient_here();
+      c->pre_valid = true;
+      c->pre_xv = c->field("coordinates").version;
+      c->pre_wv = c->field("coordinates_NM1").version;
+      c->pre_gv = c->field("cg_g").version;
+      c->pre_stage = st->stage;
     }
     return tm(0.0, total_valid);
   }
@@ -1512,7 +1554,7 @@ int pms_commit(pms_ctx* c) {
   c->R.out_u = dalloc<unsigned long long>(pms_ctx::NSLOT);
   PMS_CUDA(cudaMallocHost(&c->h_out_d, pms_ctx::NSLOT * sizeof(double)));
   PMS_CUDA(cudaMallocHost(&c->h_out_u, pms_ctx::NSLOT * sizeof(unsigned long long)));
-  c->d_coll = dalloc<double>(16);
+  c->d_coll = dalloc<double>(32);
   if (c->keep_elem) {
     c->d_elem_metric = dalloc<double>(c->Epad);
     c->d_elem_flag = dalloc<int32_t>(c->Epad);
@@ -1849,18 +1891,19 @@ int pms_total_metric_multi(pms_ctx* c, int stage, int nalpha, const double* alph
   PMS_TRY
   require_committed(c);
   if (nalpha < 1 || !alphas || !mtot) throw PmsError(PMS_ERR_ARG, "bad multi-alpha request");
-  constexpr int NB = pmsk::MULTI_ALPHA_NB;
-  for (int k0 = 0; k0 < nalpha; k0 += NB) {
-    double al[NB], m[NB];
-    uint64_t n[NB];
-    const int cnt = std::min(NB, nalpha - k0);
-    for (int k = 0; k < NB; k++) al[k] = alphas[k0 + std::min(k, cnt - 1)];
-    if (!op_total_metric_multi(c, stage, al, m, n))  // tet4 / strict build / multi-block: one pass per alpha
+  constexpr int NBMAX = pmsk::MULTI_ALPHA_NB;
+  for (int k0 = 0; k0 < nalpha;) {
+    double al[NBMAX], m[NBMAX];
+    uint64_t n[NBMAX];
+    const int left = nalpha - k0, nb = left > 8 ? NBMAX : 8, cnt = std::min(nb, left);
+    for (int k = 0; k < nb; k++) al[k] = alphas[k0 + std::min(k, cnt - 1)];
+    if (!op_total_metric_multi(c, stage, nb, al, m, n))  // tet4 / strict build / multi-block: one pass per alpha
       for (int k = 0; k < cnt; k++) op_total_metric(c, stage, al[k], &m[k], &n[k]);
     for (int k = 0; k < cnt; k++) {
       mtot[k0 + k] = m[k];
       if (n_invalid) n_invalid[k0 + k] = (size_t)n[k];
     }
+    k0 += cnt;
   }
   PMS_CATCH
 }

@@ -111,6 +111,11 @@ struct pms_ctx {
   };
   std::vector<CacheEnt> cache;
   static constexpr size_t CACHE_CAP = 32;
+  // gradient evaluated ahead of time at the end of an iteration (together with the metric the iteration returns)
+  bool pre_valid = false;
+  uint64_t pre_xv = 0, pre_wv = 0, pre_gv = 0;
+  int pre_stage = -1;
+  int spec_prev = 0;  // trial step lengths the previous line search visited (sizes the next speculative batch)
   bool speculate_line_search = true;  // evaluate the line search's alpha_init * tau^k trials in multi-alpha passes
   bool adj_fixed = false;
 

@@ -1231,10 +1231,9 @@ __global__ void __launch_bounds__(NTP, 2) k_metric_multi(const MeshDev m, const 
   grid_reduce<OpSum, 2 * NB, false>(v, 0ull, R, slot);
 }
 
-template <int FL, int STAGE>
+template <int FL, int STAGE, int NB>
 static void launch_metric_multi2(cudaStream_t st, const MeshDev& m, const double* x, const double* s, const double* w, long long stride,
                                  const double* alphas, const Reduce& R, int slot) {
-  constexpr int NB = MULTI_ALPHA_NB;
   static_assert(2 * NB <= REDUCE_MAX_NV, "reduction scratch too small");
   const size_t smem = (size_t)72 * NTP * sizeof(double);
   auto kern = k_metric_multi<FL, STAGE, NB>;
@@ -1251,19 +1250,27 @@ static void launch_metric_multi2(cudaStream_t st, const MeshDev& m, const double
   if (cap > R.max_blocks) cap = R.max_blocks;
   kern<<<(unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), NTP, smem, st>>>(m, x, s, w, stride, al, R, slot);
 }
-static bool launch_metric_multi(cudaStream_t st, const MeshDev& m, int stage, int use_ref, const double* x, const double* s,
+template <int FL, int NB>
+static void launch_metric_multi1(cudaStream_t st, const MeshDev& m, int stage, const double* x, const double* s, const double* w,
+                                 long long stride, const double* alphas, const Reduce& R, int slot) {
+  if (stage == 0)
+    launch_metric_multi2<FL, 0, NB>(st, m, x, s, w, stride, alphas, R, slot);
+  else
+    launch_metric_multi2<FL, 1, NB>(st, m, x, s, w, stride, alphas, R, slot);
+}
+static bool launch_metric_multi(cudaStream_t st, const MeshDev& m, int stage, int use_ref, int nb, const double* x, const double* s,
                                 const double* w, long long stride, const double* alphas, const Reduce& R, int slot) {
-  if (STRICT || m.kind == KIND_TET4 || (stage != 0 && !use_ref)) return false;
+  if (STRICT || m.kind == KIND_TET4 || (stage != 0 && !use_ref) || (nb != 8 && nb != 12)) return false;
   if (m.kind == KIND_SGRID) {
-    if (stage == 0)
-      launch_metric_multi2<FL_SGRID, 0>(st, m, x, s, w, stride, alphas, R, slot);
+    if (nb == 8)
+      launch_metric_multi1<FL_SGRID, 8>(st, m, stage, x, s, w, stride, alphas, R, slot);
     else
-      launch_metric_multi2<FL_SGRID, 1>(st, m, x, s, w, stride, alphas, R, slot);
+      launch_metric_multi1<FL_SGRID, 12>(st, m, stage, x, s, w, stride, alphas, R, slot);
   } else {
-    if (stage == 0)
-      launch_metric_multi2<FL_HEX8, 0>(st, m, x, s, w, stride, alphas, R, slot);
+    if (nb == 8)
+      launch_metric_multi1<FL_HEX8, 8>(st, m, stage, x, s, w, stride, alphas, R, slot);
     else
-      launch_metric_multi2<FL_HEX8, 1>(st, m, x, s, w, stride, alphas, R, slot);
+      launch_metric_multi1<FL_HEX8, 12>(st, m, stage, x, s, w, stride, alphas, R, slot);
   }
   return true;
 }

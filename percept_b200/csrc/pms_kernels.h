@@ -28,8 +28,8 @@ struct MeshDev {
   const int32_t* csr_ent32;        // same, 32-bit (when nelems*8 < 2^31): halves the gather's index traffic
 };
 
-constexpr int REDUCE_MAX_NV = 16;   // doubles one grid reduction can carry
-constexpr int MULTI_ALPHA_NB = 8;   // trial step lengths per multi-alpha metric pass
+constexpr int REDUCE_MAX_NV = 24;   // doubles one grid reduction can carry
+constexpr int MULTI_ALPHA_NB = 12;  // most trial step lengths per multi-alpha metric pass (kernels for 8 and 12)
 
 struct Reduce {  // scratch for deterministic two-level reductions (partials + last-block ticket)
   double* partial_d;            // [REDUCE_MAX_NV * max_blocks]
@@ -137,11 +137,11 @@ struct Launchers {
   // cross-rank interface sum (structured block per GPU), ascending rank order
   void (*shared_sum)(cudaStream_t, long long nshared, const int32_t* nodes, const int64_t* ptr, const int64_t* ent_pos,
                      const int32_t* ent_cnt, const double* recvbuf, double* f, int ncomp, long long stride);
-  // hex metric at MULTI_ALPHA_NB trial step lengths in one pass (line search speculation): out_d[slot + k] = metric at
-  // alphas[k], out_d[slot + NB + k] = number of invalid elements at alphas[k].  Returns false when not available
+  // hex metric at nb (8 or 12) trial step lengths in one pass (line search speculation): out_d[slot + k] = metric at
+  // alphas[k], out_d[slot + nb + k] = number of invalid elements at alphas[k].  Returns false when not available
   // (tet4, strict build, ShapeB1 without reference mesh).
-  bool (*metric_multi)(cudaStream_t, const MeshDev&, int stage, int use_ref, const double* x, const double* s, const double* w,
-                       long long stride, const double* alphas, const Reduce&, int slot);
+  bool (*metric_multi)(cudaStream_t, const MeshDev&, int stage, int use_ref, int nb, const double* x, const double* s,
+                       const double* w, long long stride, const double* alphas, const Reduce&, int slot);
   // StructuredGridRefiner: 2x prolongation of a 3-component nodal field of one block (coarse ni x nj x nk nodes at
   // src + src_off, component stride src_stride) onto the (2ni-1) x (2nj-1) x (2nk-1) block at dst + dst_off
   void (*refine_sgrid)(cudaStream_t, int ni, int nj, int nk, const double* src, long long src_off, long long src_stride,

@@ -31,13 +31,15 @@ def run(kind, nele, eps, reps=5):
         for what in ops:
             for it in range(reps + 2):
                 if it == 2: c.kernel_time_reset()
+                if what == "multi": c.total_metric_multi(stage, [0.5 * 0.5 ** k for k in range(8)]); continue
+                if what == "multi12": c.total_metric_multi(stage, [0.5 * 0.5 ** k for k in range(12)]); continue
                 if what == "metric0": c.total_metric(stage, 0.0)
                 elif what == "metricA": c.total_metric(stage, 0.5)
                 else: c.metric_and_gradient(stage)
             fam = "gradient" if what == "mgrad" else "metric"
             ms, n = c.kernel_time_ms(fam)
             ms /= reps
-            bpn = {"metric0": 48, "metricA": 72, "mgrad": 72}[what]
+            bpn = {"metric0": 48, "metricA": 72, "mgrad": 72, "multi": 72, "multi12": 72}[what]
             extra = 0 if kind == "sgrid" else (32 if kind == "hex8" else 16) * ne
             gb = (bpn * nnod + extra) / 1e9
             print(f"stage {stage} {what:8s}: {ms:8.3f} ms  {ne/ms/1e6:8.2f} Gelem/s  alg {gb/ms*1e3:7.1f} GB/s ({gb/ms*1e3/6561.6*100:5.1f}% of 6561.6)")
