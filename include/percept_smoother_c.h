@@ -111,6 +111,12 @@ int pms_field_upload(pms_ctx* ctx, const char* name, int block, const double* ho
 int pms_field_download(pms_ctx* ctx, const char* name, int block, double* host, int layout);
 /* Device view of a field: component c of local node n is dptr[c*comp_stride+n]. */
 int pms_field_device_ptr(pms_ctx* ctx, const char* name, double** dptr, size_t* comp_stride);
+/* Asynchronous SoA download (pinned host memory): returns at once, the copy runs on a second stream after everything
+ * queued so far and beside later pms_field_upload calls (PCIe is full duplex); kernels queued afterwards wait for it.
+ * pms_transfer_wait blocks until the host buffer is complete.  Lets a caller that evaluates many coordinate sets
+ * overlap the gradient read-back of one evaluation with the coordinate upload of the next.                        */
+int pms_field_download_async(pms_ctx* ctx, const char* name, int block, double* host);
+int pms_transfer_wait(pms_ctx* ctx);
 /* BLAS-1: PerceptMesh::copy_field / nodal_field_* (PerceptMesh.cpp:4571-4820),
  * SB_* functors (structured/BlockStructuredGrid.cpp:301-578).                  */
 int pms_copy_field(pms_ctx* ctx, const char* dst, const char* src);

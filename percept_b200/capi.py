@@ -89,6 +89,8 @@ class Api:
     }
     # product-only entry points (absent from the oracle twin)
     _SIGS_PRODUCT = {
+        "field_download_async": [C.c_char_p, C.c_int, _dp],
+        "transfer_wait": [],
         "total_metric_multi": [C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_size_t)],
         "field_device_ptr": [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
         "comm_init": [C.c_void_p, C.c_int, C.c_int],
@@ -284,6 +286,15 @@ class Ctx:
             out = np.empty((nc, n) if layout == SOA else (n, nc), dtype=np.float64)
         self._call("field_download", name.encode(), int(block), _dptr(out), int(layout))
         return out
+
+    def download_async(self, name, out, block=-1):
+        """SoA download into the (pinned) array `out` on a second stream; call transfer_wait() before reading it."""
+        nc = 3 if name in FIELDS3 else 1
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == nc * self._nblock(block)
+        self._call("field_download_async", name.encode(), int(block), _dptr(out))
+
+    def transfer_wait(self):
+        self._call("transfer_wait")
 
     def copy_field(self, dst, src):
         self._call("copy_field", dst.encode(), src.encode())

@@ -45,6 +45,10 @@ struct Timed {
   int fam;
   cudaEvent_t a = nullptr, b = nullptr;
   Timed(pms_ctx* cc, int f, int nlaunch = 1) : c(cc), fam(f) {
+    if (c->copy_pending) {  // kernels may overwrite the field an asynchronous download is still reading
+      cudaStreamWaitEvent(c->stream, c->copy_done, 0);
+      c->copy_pending = false;
+    }
     c->launches += nlaunch;
     c->fam_launches[fam] += nlaunch;
     if (c->timing) {
@@ -1157,6 +1161,12 @@ void pms_destroy(pms_ctx* c) {
     }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    if (c->copy_stream) {
+      cudaStreamSynchronize(c->copy_stream);
+      cudaStreamDestroy(c->copy_stream);
+      cudaEventDestroy(c->copy_done);
+      cudaEventDestroy(c->copy_ready);
+    }
     cudaStreamDestroy(c->stream);
   }
   delete c;
@@ -1604,6 +1614,10 @@ int pms_field_upload(pms_ctx* c, const char* name, int block, const double* host
   DField& f = c->field(name);
   long long off, n;
   block_range(c, block, off, n);
+  if (c->copy_pending && c->copy_field_name == name) {
+    PMS_CUDA(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
+    c->copy_pending = false;
+  }
   if (layout == PMS_SOA) {
     for (int k = 0; k < f.ncomp; k++)
       PMS_CUDA(cudaMemcpyAsync(f.d + (size_t)k * c->Npad + off, host + (size_t)k * n, n * sizeof(double),
@@ -1644,6 +1658,35 @@ int pms_field_download(pms_ctx* c, const char* name, int block, double* host, in
       for (long long i = 0; i < n; i++) host[(size_t)i * f.ncomp + k] = tmp[(size_t)k * n + i];
   } else
     throw PmsError(PMS_ERR_ARG, "bad layout");
+  PMS_CATCH
+}
+
+// Asynchronous download on a second stream: returns at once; the copy starts when everything queued on the ctx stream so
+// far has finished and runs beside later uploads (PCIe is full duplex).  Kernels queued afterwards wait for it.
+int pms_field_download_async(pms_ctx* c, const char* name, int block, double* host) {
+  PMS_TRY
+  require_committed(c);
+  DField& f = c->field(name);
+  long long off, n;
+  block_range(c, block, off, n);
+  if (!c->copy_stream) {
+    PMS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    PMS_CUDA(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
+    PMS_CUDA(cudaEventCreateWithFlags(&c->copy_ready, cudaEventDisableTiming));
+  }
+  PMS_CUDA(cudaEventRecord(c->copy_ready, c->stream));
+  PMS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_ready, 0));
+  for (int k = 0; k < f.ncomp; k++)
+    PMS_CUDA(cudaMemcpyAsync(host + (size_t)k * n, f.d + (size_t)k * c->Npad + off, n * sizeof(double), cudaMemcpyDeviceToHost,
+                             c->copy_stream));
+  PMS_CUDA(cudaEventRecord(c->copy_done, c->copy_stream));
+  c->copy_pending = true;
+  c->copy_field_name = name;
+  PMS_CATCH
+}
+int pms_transfer_wait(pms_ctx* c) {
+  PMS_TRY
+  if (c->copy_stream) PMS_CUDA(cudaStreamSynchronize(c->copy_stream));
   PMS_CATCH
 }
 

@@ -135,6 +135,12 @@ struct pms_ctx {
   double *d_if_send = nullptr, *d_if_recv = nullptr;
   long long n_shared = 0;
 
+  // asynchronous result download (second stream, so a device->host copy can run beside the next host->device upload)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_done = nullptr, copy_ready = nullptr;
+  bool copy_pending = false;
+  std::string copy_field_name;
+
   // instrumentation
   uint64_t launches = 0;
   double fam_ms[FAM_COUNT] = {0};

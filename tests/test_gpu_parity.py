@@ -467,6 +467,33 @@ def test_brick_gradient_on_irregular_meshes(mesh, variant):
     g.set_option("variant_grad_corners", 2)
 
 
+def test_async_download_overlaps_next_upload_without_corrupting_results():
+    """pms_field_download_async: the read-back of evaluation k must see evaluation k's gradient even though the next
+    coordinates are uploaded and the next evaluation is queued before the copy is waited for."""
+    g, _ = pair("hex8", 24, 0.25, strict=0)
+    X0 = g.download("coordinates").copy()
+    rng = np.random.default_rng(1)
+    fixed = meshes.boundary_mask(25) != 0
+    ref, outs = [], []
+    Xs = [np.ascontiguousarray(X0 + 1e-3 * rng.standard_normal(X0.shape) * (~fixed)[None, :]) for _ in range(4)]
+    for X in Xs:
+        g.upload("coordinates", X)
+        g.metric_and_gradient(1)
+        ref.append(g.download("cg_g").copy())
+    g.upload("coordinates", Xs[0])
+    g.metric_and_gradient(1)
+    for k in range(1, 5):
+        buf = np.empty_like(X0)
+        g.download_async("cg_g", buf)           # gradient of evaluation k-1
+        if k < 4:
+            g.upload("coordinates", Xs[k])
+            g.metric_and_gradient(1)
+        outs.append(buf)
+    g.transfer_wait()
+    for a, b in zip(ref, outs):
+        assert np.array_equal(a, b)
+
+
 def _outcome(ctx, niter, tol):
     """(status, payload): run_algorithm result or the error text the reference would throw."""
     try:
