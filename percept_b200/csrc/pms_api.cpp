@@ -841,11 +841,21 @@ struct Driver {
   // Pass fusion (with line-search speculation on): the fused metric+gradient kernel's metric is put in the metric cache
   // as the alpha = 0 value at these coordinates, and a gradient computed at the end of the previous iteration is reused.
   bool fuse_passes() const { return c->speculate_line_search && c->cache_metric && !c->keep_elem && c->use_ref_mesh && !c->strict_fp; }
-  void gradient_here() {
+  bool pre_matches() const {
+    return c->pre_valid && c->pre_xv == c->field("coordinates").version && c->pre_wv == c->field("coordinates_NM1").version &&
+           c->pre_gv == c->field("cg_g").version && c->pre_stage == st->stage && fuse_passes();
+  }
+  void mark_pre() {
+    c->pre_valid = true;
+    c->pre_xv = c->field("coordinates").version;
+    c->pre_wv = c->field("coordinates_NM1").version;
+    c->pre_gv = c->field("cg_g").version;
+    c->pre_stage = st->stage;
+  }
+  void gradient_here(double* m_out = nullptr, uint64_t* n_out = nullptr) {
     DField& X = c->field("coordinates");
     DField& W = c->field("coordinates_NM1");
-    if (c->pre_valid && c->pre_xv == X.version && c->pre_wv == W.version && c->pre_gv == c->field("cg_g").version &&
-        c->pre_stage == st->stage && fuse_passes()) {
+    if (pre_matches()) {
       c->pre_valid = false;
       return;  // cg_g already holds f'(x) for these coordinates
     }
@@ -853,6 +863,8 @@ struct Driver {
     double m;
     uint64_t n;
     op_gradient(c, st->stage, &m, &n, /*write_r=*/false);  // cg_r = cg_g (Def.hpp:1508) is overwritten by r = -g
+    if (m_out) *m_out = m;
+    if (n_out) *n_out = n;
     st->n_gradient_evals++;
     // (a metric of exactly 0 is the reference's early-exit test `metric_check == 0.0`, Def.hpp:1041: at that noise floor the
     //  metric kernel's own value decides, as without fusion)
@@ -873,7 +885,9 @@ struct Driver {
   }
 
   // line_search, Def.hpp:466-591
+  bool moved = false;  // line_search already applied the accepted step (update_node_positions) and holds f'(x_new)
   double line_search(bool& restarted) {
+    moved = false;
     const double alpha_fac = 10.0, tau = 0.5, c0 = 1.e-1, min_alpha_factor = 1.e-12;
     st->alpha_0 = op_alpha0(c);
     double alpha = alpha_fac * st->alpha_0;
@@ -945,8 +959,26 @@ struct Driver {
     if (std::fabs(den) > 1.e-10) {
       const double alpha_quadratic = num / den;
       if (alpha_quadratic > 1.e-10 && alpha_quadratic < 2 * alpha) {
-        const double fm = tm(alpha_quadratic, total_valid);
-        if (fm < f2 && (st->stage == 0 || total_valid)) alpha = alpha_quadratic;
+        if (fuse_passes() && !c->smooth_surfaces) {
+          // The quadratic step is accepted almost always, and an accepted step is followed by the update and by the
+          // fused metric+gradient pass at the new coordinates.  So move there first and let that pass provide fm;
+          // only a rejected step costs extra (restore x from coordinates_lagged).
+          op_update(c, alpha_quadratic, &st->dmax, &st->dmax_relative);
+          double fm = 0.0;
+          uint64_t nq = 0;
+          c->pre_valid = false;
+          gradient_here(&fm, &nq);
+          if (fm < f2 && (st->stage == 0 || nq == 0)) {
+            alpha = alpha_quadratic;
+            mark_pre();
+            moved = true;
+          } else {
+            op_copy(c, "coordinates", "coordinates_lagged");
+          }
+        } else {
+          const double fm = tm(alpha_quadratic, total_valid);
+          if (fm < f2 && (st->stage == 0 || total_valid)) alpha = alpha_quadratic;
+        }
       }
     }
     return alpha;
@@ -1015,7 +1047,7 @@ struct Driver {
     const double snorm = op_dot(c, "cg_s", "cg_s");
     st->grad_norm_scaled = st->alpha_0 * std::sqrt(snorm) / double(st->num_nodes);
     st->alpha = alpha;
-    op_update(c, alpha, &st->dmax, &st->dmax_relative);  // update_node_positions, Def.hpp:395-410
+    if (!moved) op_update(c, alpha, &st->dmax, &st->dmax_relative);  // update_node_positions, Def.hpp:395-410
     if (c->smooth_surfaces) {  // check if re-snapped geometry is acceptable, Def.hpp:1078-1089
       op_snap_nodes(c);
       if (st->stage != 0) {
@@ -1027,13 +1059,11 @@ struct Driver {
     if (fuse_passes()) {
       // the metric at the new coordinates comes from the fused metric+gradient pass whose gradient the next
       // iteration starts with (same x): one pass instead of a metric pass now and a gradient pass then
-      c->pre_valid = false;
-      gradient_here();
-      c->pre_valid = true;
-      c->pre_xv = c->field("coordinates").version;
-      c->pre_wv = c->field("coordinates_NM1").version;
-      c->pre_gv = c->field("cg_g").version;
-      c->pre_stage = st->stage;
+      if (!pre_matches()) {
+        c->pre_valid = false;
+        gradient_here();
+        mark_pre();
+      }
     }
     return tm(0.0, total_valid);
   }
