@@ -66,6 +66,15 @@ struct SmemVerts {  // vertices read in place from a thread-private shared-memor
   }
 };
 
+template <bool EXODUS, int STRIDE>
+struct SmemVertsReload {  // as SmemVerts, but every access is a fresh LDS: no vertex value stays live across corners
+  const volatile double* base;
+  PMS_DI explicit SmemVertsReload(const double* b) : base(b) {}
+  PMS_DI double operator()(int p, int r) const {
+    const int a = EXODUS ? (p == 2 ? 3 : (p == 3 ? 2 : (p == 6 ? 7 : (p == 7 ? 6 : p)))) : p;
+    return base[(a * 3 + r) * STRIDE];
+  }
+};
 template <int NN>
 struct IdxVerts {  // vertices of a brick staged once per distinct node: base[r*NN + local node index]
   const double* base;

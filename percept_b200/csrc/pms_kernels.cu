@@ -1160,12 +1160,15 @@ static void launch_metric_occ(cudaStream_t st, const MeshDev& m, const double* x
 // pass evaluates NB of them (hex_metric_multi: per-corner polynomial coefficients once, ~20 FP64 per extra alpha).
 // Vertices of x, s, w stay in the thread's shared-memory column (in place, single buffer, 2 CTAs/SM interleave).
 // ------------------------------------------------------------------------------------------------
+#ifndef MULTI_MINB
+#define MULTI_MINB 2
+#endif
 template <int NB>
 struct AlphaPack {
   double a[NB];
 };
 template <int FL, int STAGE, int NB>
-__global__ void __launch_bounds__(NTP, 2) k_metric_multi(const MeshDev m, const double* __restrict__ x, const double* __restrict__ s,
+__global__ void __launch_bounds__(NTP, MULTI_MINB) k_metric_multi(const MeshDev m, const double* __restrict__ x, const double* __restrict__ s,
                                                          const double* __restrict__ w, const long long stride,
                                                          const AlphaPack<NB> al, const Reduce R, const int slot) {
   extern __shared__ double sm[];  // [72][NTP]
@@ -1206,6 +1209,8 @@ __global__ void __launch_bounds__(NTP, 2) k_metric_multi(const MeshDev m, const 
 #pragma unroll
         for (int r = 0; r < 3; r++) *slot_in(2, a, r) = 0.0;
       }
+    // (measured alternatives, both slower: reloading accessors SmemVertsReload without spills at 2 CTAs/SM 4.30 ms, or at
+    //  168 registers / 3 CTAs/SM 4.61 ms, vs 3.63 ms for 8 alphas at 256^3 with the values kept in registers)
     const SmemVerts<FL == FL_HEX8, NTP> VC(slot_in(0, 0, 0)), VO(slot_in(1, 0, 0)), VS(slot_in(2, 0, 0));
     bool counted = true;
     if (FL != FL_SGRID && m.elem_owned) counted = m.elem_owned[e] != 0;
