@@ -67,7 +67,17 @@ const char* pms_last_error(const pms_ctx* ctx);
  *                  expression order (bit-comparable with a -ffp-contract=off
  *                  CPU build); 0 = contracted FMA build (default)
  *  "cache_metric"  1 = driver reuses bitwise-identical metric evaluations
- *                  (SURVEY 3.3), 0 = evaluate exactly as often as the reference */
+ *                  (SURVEY 3.3), 0 = evaluate exactly as often as the reference
+ *  "speculate_line_search"  default 1 (needs cache_metric 1, hex meshes, default build): the driver evaluates the
+ *                  backtracking sequence alpha_init*tau^k in multi-alpha passes (pms_total_metric_multi), takes the
+ *                  metric at the new coordinates from the fused metric+gradient pass and keeps that gradient for the
+ *                  next iteration, and tests the quadratic step by moving there.  Same decisions and iteration
+ *                  counts; values agree to rounding (<= 1e-12) instead of bitwise.  Side effect: after
+ *                  pms_run_one_iteration the field cg_g holds f'(x_new) (the gradient the next iteration starts
+ *                  from) instead of f'(x_old).  0 = the reference's literal pass sequence.
+ *  "smooth_surfaces"  (PerceptMesh::get_smooth_surfaces) default 0, see the surface smoothing hooks below
+ *  "keep_element_metrics"  1 = metric passes also store per-element values for pms_get_element_metrics
+ *  "variant_metric_corners" / "variant_grad_corners"  kernel variants (tuning aid)             */
 int pms_set_option(pms_ctx* ctx, const char* key, double value);
 
 /* ---- mesh definition ---------------------------------------------------- */
