@@ -308,31 +308,34 @@ def run_ours(args):
     e2e_sync = total_elems * e2e_steps / float(dt.item()) / 1e6
     log(f"e2e loop (one evaluation at a time) done: {e2e_sync:.0f} Melem/s")
 
-    # pipelined over consecutive evaluations: every step still uploads its coordinates and downloads its gradient,
-    # but the gradient read-back of evaluation k (second stream) runs beside the coordinate upload of evaluation k+1
+    # pipelined over consecutive evaluations: every step still uploads its coordinates and downloads its gradient, but
+    # the read-back of evaluation k (second stream) and the upload of evaluation k+2 (third stream) run beside the
+    # kernels of evaluation k+1 (device staging buffers on both sides, see pms_field_*_async)
     hg2 = torch.empty((3, nnod_local), dtype=torch.float64).pin_memory()
     hbuf = [hg_np, hg2.numpy()]
-    ctx.upload("coordinates", hx_np)
-    ctx.metric_and_gradient(STAGE)
-    for k in range(2):
-        ctx.download_async("cg_g", hbuf[k % 2])
-        ctx.upload("coordinates", hx_np)
-        ctx.metric_and_gradient(STAGE)
-    ctx.transfer_wait()
+
+    def pipelined(nsteps):
+        ctx.upload("coordinates", hx_np)                 # input of evaluation 0
+        ctx.metric_and_gradient(STAGE)                   # evaluation 0
+        ctx.upload_async("coordinates", hx_np)           # input of evaluation 1 on its way
+        for k in range(nsteps):
+            ctx.download_async("cg_g", hbuf[k % 2])      # D2H 24 B/node: gradient of evaluation k
+            ctx.upload_finish()                          # coordinates <- staged input of evaluation k+1
+            ctx.upload_async("coordinates", hx_np)       # H2D 24 B/node: input of evaluation k+2
+            ctx.metric_and_gradient(STAGE)               # evaluation k+1 (+ D2H of {mtot, n_invalid})
+        ctx.upload_finish()
+        ctx.transfer_wait()
+    pipelined(2)
     barrier()
     t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        ctx.download_async("cg_g", hbuf[k % 2])         # D2H 24 B/node, result of the previous evaluation
-        ctx.upload("coordinates", hx_np)                # H2D 24 B/node, input of this evaluation
-        m, ni = ctx.metric_and_gradient(STAGE)          # kernels (wait for the read-back) + D2H of {mtot, n_invalid}
-    ctx.transfer_wait()
+    pipelined(e2e_steps)                                 # e2e_steps+1 uploads+evaluations, e2e_steps read-backs timed
     barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_val = total_elems * e2e_steps / float(dt.item()) / 1e6
-    assert np.array_equal(hbuf[0], hbuf[1])             # same coordinates every step: identical gradients came back
-    log(f"e2e loop (read-back overlapped with the next upload) done: {e2e_val:.0f} Melem/s")
+    assert np.array_equal(hbuf[0], hbuf[1])              # same coordinates every step: identical gradients came back
+    log(f"e2e loop (transfers overlapped with the kernels of the neighbouring evaluations) done: {e2e_val:.0f} Melem/s")
 
     # ---- (3) CG iterations/s (device resident; the reference's run_one_iteration incl. line search) ------------
     cg = {}
@@ -402,7 +405,7 @@ def run_ours(args):
                    "global_cells": [NX, NY, NZ], "partition": f"{px}x{py}x{pz} boxes, 1 ghost layer, owner-computes",
                    "l2": "inputs (815 MB of coordinates per GPU) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_val, "unit": "Melem/s", "h2d_bytes_per_step": 24 * nnod_local, "d2h_bytes_per_step": 24 * nnod_local + 16,
-                "steps": e2e_steps, "api": "per step: pms_field_download_async(cg_g of the previous evaluation) || pms_field_upload(coordinates) + pms_metric_and_gradient; pinned host buffers, two streams",
+                "steps": e2e_steps, "api": "per step: pms_field_download_async(cg_g of evaluation k) || pms_field_upload_async(coordinates of k+2) || pms_metric_and_gradient(k+1); pinned host buffers, three streams",
                 "one_evaluation_at_a_time": e2e_sync},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "cg": cg, "check": {"total_metric": mtot, "n_invalid": int(ninv)}, "setup_s": t_setup,

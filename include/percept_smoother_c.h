@@ -121,11 +121,16 @@ int pms_field_upload(pms_ctx* ctx, const char* name, int block, const double* ho
 int pms_field_download(pms_ctx* ctx, const char* name, int block, double* host, int layout);
 /* Device view of a field: component c of local node n is dptr[c*comp_stride+n]. */
 int pms_field_device_ptr(pms_ctx* ctx, const char* name, double** dptr, size_t* comp_stride);
-/* Asynchronous SoA download (pinned host memory): returns at once, the copy runs on a second stream after everything
- * queued so far and beside later pms_field_upload calls (PCIe is full duplex); kernels queued afterwards wait for it.
- * pms_transfer_wait blocks until the host buffer is complete.  Lets a caller that evaluates many coordinate sets
- * overlap the gradient read-back of one evaluation with the coordinate upload of the next.                        */
+/* Asynchronous SoA transfers (pinned host memory) for callers that evaluate many coordinate sets: the read-back of one
+ * evaluation and the upload of a later one run beside the kernels (PCIe is full duplex; three streams).  Both go through
+ * device staging buffers, so kernels queued afterwards never race with a copy in flight.
+ *  pms_field_download_async: snapshots the field on the ctx stream and copies the snapshot to `host` on a second stream;
+ *                            pms_transfer_wait blocks until the host buffer(s) are complete.
+ *  pms_field_upload_async:   starts host -> staging at once (third stream); the field itself changes only when
+ *                            pms_field_upload_finish is called (stream-ordered, does not block the host).            */
 int pms_field_download_async(pms_ctx* ctx, const char* name, int block, double* host);
+int pms_field_upload_async(pms_ctx* ctx, const char* name, int block, const double* host);
+int pms_field_upload_finish(pms_ctx* ctx);
 int pms_transfer_wait(pms_ctx* ctx);
 /* BLAS-1: PerceptMesh::copy_field / nodal_field_* (PerceptMesh.cpp:4571-4820),
  * SB_* functors (structured/BlockStructuredGrid.cpp:301-578).                  */

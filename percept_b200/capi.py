@@ -90,6 +90,8 @@ class Api:
     # product-only entry points (absent from the oracle twin)
     _SIGS_PRODUCT = {
         "field_download_async": [C.c_char_p, C.c_int, _dp],
+        "field_upload_async": [C.c_char_p, C.c_int, _dp],
+        "field_upload_finish": [],
         "transfer_wait": [],
         "total_metric_multi": [C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_size_t)],
         "field_device_ptr": [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
@@ -292,6 +294,15 @@ class Ctx:
         nc = 3 if name in FIELDS3 else 1
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == nc * self._nblock(block)
         self._call("field_download_async", name.encode(), int(block), _dptr(out))
+
+    def upload_async(self, name, arr, block=-1):
+        """start host -> device staging on a side stream; the field changes at upload_finish()."""
+        nc = 3 if name in FIELDS3 else 1
+        assert arr.dtype == np.float64 and arr.flags.c_contiguous and arr.size == nc * self._nblock(block)
+        self._call("field_upload_async", name.encode(), int(block), _dptr(arr))
+
+    def upload_finish(self):
+        self._call("field_upload_finish")
 
     def transfer_wait(self):
         self._call("transfer_wait")

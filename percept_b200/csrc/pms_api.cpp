@@ -45,10 +45,6 @@ struct Timed {
   int fam;
   cudaEvent_t a = nullptr, b = nullptr;
   Timed(pms_ctx* cc, int f, int nlaunch = 1) : c(cc), fam(f) {
-    if (c->copy_pending) {  // kernels may overwrite the field an asynchronous download is still reading
-      cudaStreamWaitEvent(c->stream, c->copy_done, 0);
-      c->copy_pending = false;
-    }
     c->launches += nlaunch;
     c->fam_launches[fam] += nlaunch;
     if (c->timing) {
@@ -1191,11 +1187,14 @@ void pms_destroy(pms_ctx* c) {
     }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
-    if (c->copy_stream) {
-      cudaStreamSynchronize(c->copy_stream);
-      cudaStreamDestroy(c->copy_stream);
-      cudaEventDestroy(c->copy_done);
-      cudaEventDestroy(c->copy_ready);
+    if (c->d2h_stream) {
+      cudaStreamSynchronize(c->d2h_stream);
+      cudaStreamSynchronize(c->h2d_stream);
+      cudaStreamDestroy(c->d2h_stream);
+      cudaStreamDestroy(c->h2d_stream);
+      for (cudaEvent_t e : {c->ev_out_ready, c->ev_out_done, c->ev_in_done, c->ev_in_free}) cudaEventDestroy(e);
+      if (c->stage_out) cudaFree(c->stage_out);
+      if (c->stage_in) cudaFree(c->stage_in);
     }
     cudaStreamDestroy(c->stream);
   }
@@ -1644,10 +1643,6 @@ int pms_field_upload(pms_ctx* c, const char* name, int block, const double* host
   DField& f = c->field(name);
   long long off, n;
   block_range(c, block, off, n);
-  if (c->copy_pending && c->copy_field_name == name) {
-    PMS_CUDA(cudaStreamWaitEvent(c->stream, c->copy_done, 0));
-    c->copy_pending = false;
-  }
   if (layout == PMS_SOA) {
     for (int k = 0; k < f.ncomp; k++)
       PMS_CUDA(cudaMemcpyAsync(f.d + (size_t)k * c->Npad + off, host + (size_t)k * n, n * sizeof(double),
@@ -1691,32 +1686,75 @@ int pms_field_download(pms_ctx* c, const char* name, int block, double* host, in
   PMS_CATCH
 }
 
-// Asynchronous download on a second stream: returns at once; the copy starts when everything queued on the ctx stream so
-// far has finished and runs beside later uploads (PCIe is full duplex).  Kernels queued afterwards wait for it.
+// Asynchronous transfers.  Both go through a device staging buffer, so kernels queued later never race with a copy:
+// download: field -> stage_out on the ctx stream (D2D), then stage_out -> host on a second stream;
+// upload:   host -> stage_in on a third stream at once, stage_in -> field on the ctx stream at pms_field_upload_finish.
+static void ensure_transfer_streams(pms_ctx* c) {
+  if (c->d2h_stream) return;
+  PMS_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  PMS_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&c->ev_out_ready, &c->ev_out_done, &c->ev_in_done, &c->ev_in_free})
+    PMS_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+}
 int pms_field_download_async(pms_ctx* c, const char* name, int block, double* host) {
   PMS_TRY
   require_committed(c);
   DField& f = c->field(name);
   long long off, n;
   block_range(c, block, off, n);
-  if (!c->copy_stream) {
-    PMS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    PMS_CUDA(cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming));
-    PMS_CUDA(cudaEventCreateWithFlags(&c->copy_ready, cudaEventDisableTiming));
-  }
-  PMS_CUDA(cudaEventRecord(c->copy_ready, c->stream));
-  PMS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_ready, 0));
+  ensure_transfer_streams(c);
+  if (!c->stage_out) c->stage_out = dalloc<double>((size_t)3 * c->Npad);
+  if (c->out_pending) PMS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_out_done, 0));  // previous read-back still uses stage_out
   for (int k = 0; k < f.ncomp; k++)
-    PMS_CUDA(cudaMemcpyAsync(host + (size_t)k * n, f.d + (size_t)k * c->Npad + off, n * sizeof(double), cudaMemcpyDeviceToHost,
-                             c->copy_stream));
-  PMS_CUDA(cudaEventRecord(c->copy_done, c->copy_stream));
-  c->copy_pending = true;
-  c->copy_field_name = name;
+    PMS_CUDA(cudaMemcpyAsync(c->stage_out + (size_t)k * c->Npad, f.d + (size_t)k * c->Npad + off, n * sizeof(double),
+                             cudaMemcpyDeviceToDevice, c->stream));
+  PMS_CUDA(cudaEventRecord(c->ev_out_ready, c->stream));
+  PMS_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_out_ready, 0));
+  for (int k = 0; k < f.ncomp; k++)
+    PMS_CUDA(cudaMemcpyAsync(host + (size_t)k * n, c->stage_out + (size_t)k * c->Npad, n * sizeof(double), cudaMemcpyDeviceToHost,
+                             c->d2h_stream));
+  PMS_CUDA(cudaEventRecord(c->ev_out_done, c->d2h_stream));
+  c->out_pending = true;
+  PMS_CATCH
+}
+int pms_field_upload_async(pms_ctx* c, const char* name, int block, const double* host) {
+  PMS_TRY
+  require_committed(c);
+  DField& f = c->field(name);
+  long long off, n;
+  block_range(c, block, off, n);
+  if (c->in_pending) throw PmsError(PMS_ERR_ARG, "an asynchronous upload is already in flight: call pms_field_upload_finish first");
+  ensure_transfer_streams(c);
+  if (!c->stage_in) c->stage_in = dalloc<double>((size_t)3 * c->Npad);
+  PMS_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->ev_in_free, 0));  // (no-op until recorded) stage_in was consumed
+  for (int k = 0; k < f.ncomp; k++)
+    PMS_CUDA(cudaMemcpyAsync(c->stage_in + (size_t)k * c->Npad, host + (size_t)k * n, n * sizeof(double), cudaMemcpyHostToDevice,
+                             c->h2d_stream));
+  PMS_CUDA(cudaEventRecord(c->ev_in_done, c->h2d_stream));
+  c->in_pending = true;
+  c->in_field = name;
+  c->in_block = block;
+  PMS_CATCH
+}
+int pms_field_upload_finish(pms_ctx* c) {
+  PMS_TRY
+  if (!c->in_pending) throw PmsError(PMS_ERR_ARG, "no asynchronous upload in flight");
+  DField& f = c->field(c->in_field.c_str());
+  long long off, n;
+  block_range(c, c->in_block, off, n);
+  PMS_CUDA(cudaStreamWaitEvent(c->stream, c->ev_in_done, 0));
+  for (int k = 0; k < f.ncomp; k++)
+    PMS_CUDA(cudaMemcpyAsync(f.d + (size_t)k * c->Npad + off, c->stage_in + (size_t)k * c->Npad, n * sizeof(double),
+                             cudaMemcpyDeviceToDevice, c->stream));
+  PMS_CUDA(cudaEventRecord(c->ev_in_free, c->stream));
+  f.version++;
+  c->in_pending = false;
   PMS_CATCH
 }
 int pms_transfer_wait(pms_ctx* c) {
   PMS_TRY
-  if (c->copy_stream) PMS_CUDA(cudaStreamSynchronize(c->copy_stream));
+  if (c->d2h_stream) PMS_CUDA(cudaStreamSynchronize(c->d2h_stream));
+  c->out_pending = false;
   PMS_CATCH
 }
 

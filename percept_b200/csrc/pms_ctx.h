@@ -135,11 +135,15 @@ struct pms_ctx {
   double *d_if_send = nullptr, *d_if_recv = nullptr;
   long long n_shared = 0;
 
-  // asynchronous result download (second stream, so a device->host copy can run beside the next host->device upload)
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t copy_done = nullptr, copy_ready = nullptr;
-  bool copy_pending = false;
-  std::string copy_field_name;
+  // asynchronous transfers through device staging buffers (so no kernel ever races with a copy in flight):
+  //   download: field -> stage_out (D2D, ctx stream) -> host (D2H, d2h_stream)
+  //   upload:   host -> stage_in (H2D, h2d_stream), later stage_in -> field (D2D, ctx stream) at upload_finish
+  cudaStream_t d2h_stream = nullptr, h2d_stream = nullptr;
+  cudaEvent_t ev_out_ready = nullptr, ev_out_done = nullptr, ev_in_done = nullptr, ev_in_free = nullptr;
+  double *stage_out = nullptr, *stage_in = nullptr;
+  bool out_pending = false, in_pending = false;
+  std::string in_field;
+  int in_block = -1;
 
   // instrumentation
   uint64_t launches = 0;

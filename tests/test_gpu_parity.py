@@ -492,6 +492,23 @@ def test_async_download_overlaps_next_upload_without_corrupting_results():
     g.transfer_wait()
     for a, b in zip(ref, outs):
         assert np.array_equal(a, b)
+    # fully pipelined form: upload of evaluation k+2 and read-back of k beside the kernels of k+1
+    outs = [np.empty_like(X0) for _ in range(4)]
+    g.upload("coordinates", Xs[0])
+    g.metric_and_gradient(1)
+    g.upload_async("coordinates", Xs[1])
+    for k in range(3):
+        g.download_async("cg_g", outs[k])
+        g.upload_finish()
+        if k + 2 < 4:
+            g.upload_async("coordinates", Xs[k + 2])
+        g.metric_and_gradient(1)
+    g.download_async("cg_g", outs[3])
+    g.transfer_wait()
+    for a, b in zip(ref, outs):
+        assert np.array_equal(a, b)
+    with pytest.raises(pb.SmootherError):
+        g.upload_finish()  # nothing in flight
 
 
 def _outcome(ctx, niter, tol):
