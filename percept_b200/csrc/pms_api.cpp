@@ -117,7 +117,7 @@ struct Nccl {
   const char* (*GetErrorString)(int) = nullptr;
 };
 Nccl g_nccl;
-constexpr int NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3;
+constexpr int NCCL_F64 = 8, NCCL_U64 = 5, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3;
 
 void nccl_load() {
   if (g_nccl.h) return;
@@ -157,6 +157,19 @@ void allreduce(pms_ctx* c, double* v, int n, int op) {
   }
   PMS_CUDA(cudaMemcpyAsync(v, c->d_coll, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   PMS_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// Results of a grid reduction, combined across ranks ON THE DEVICE (in place in the result slots) and then read back
+// once: one stream synchronisation per scalar instead of D2H + H2D + allreduce + D2H.
+void fetch_reduced(pms_ctx* c, int slot, int nd, int nu, int op) {
+  if (c->nranks > 1) {
+    Timed t(c, FAM_HALO);
+    PMS_NCCL(g_nccl.GroupStart());
+    if (nd) PMS_NCCL(g_nccl.AllReduce(c->R.out_d + slot, c->R.out_d + slot, nd, NCCL_F64, op, c->nccl_comm, c->stream));
+    if (nu) PMS_NCCL(g_nccl.AllReduce(c->R.out_u + slot, c->R.out_u + slot, nu, NCCL_U64, NCCL_SUM, c->nccl_comm, c->stream));
+    PMS_NCCL(g_nccl.GroupEnd());
+  }
+  fetch(c, slot, nd, nu);
 }
 
 template <class T>
@@ -237,10 +250,8 @@ double op_dot(pms_ctx* c, const char* x, const char* y) {
     c->L->dot(c->stream, fx.d, fy.d, c->dotmask_trivial ? nullptr : c->d_dotmask, c->N, c->Npad, fx.ncomp, c->R, 0);
     check_launch(c, "dot");
   }
-  fetch(c, 0, 1, 0);
-  double v = c->h_out_d[0];
-  allreduce(c, &v, 1, NCCL_SUM);
-  return v;
+  fetch_reduced(c, 0, 1, 0, NCCL_SUM);
+  return c->h_out_d[0];
 }
 
 void halo_exchange(pms_ctx* c, const char* name);
@@ -270,18 +281,12 @@ void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t
                  c->d_fixed);
     check_launch(c, "metric");
   }
-  fetch(c, 0, nb, nb);
+  fetch_reduced(c, 0, nb, nb, NCCL_SUM);
   double m = 0.0;  // per-block results added in block order (Def.hpp:355-360)
   uint64_t n = 0;
   for (int b = 0; b < nb; b++) {
     m += c->h_out_d[b];
     n += c->h_out_u[b];
-  }
-  if (c->nranks > 1) {
-    double v[2] = {m, (double)n};
-    allreduce(c, v, 2, NCCL_SUM);
-    m = v[0];
-    n = (uint64_t)v[1];
   }
   *mtot = m;
   if (ninv) *ninv = n;
@@ -308,10 +313,9 @@ bool op_total_metric_multi(pms_ctx* c, int stage, int nb, const double* alphas, 
     }
     check_launch(c, "metric_multi");
   }
-  fetch(c, 0, 2 * nb, 0);
+  fetch_reduced(c, 0, 2 * nb, 0, NCCL_SUM);
   double v[2 * pmsk::MULTI_ALPHA_NB];
   for (int k = 0; k < 2 * nb; k++) v[k] = c->h_out_d[k];
-  allreduce(c, v, 2 * nb, NCCL_SUM);
   for (int k = 0; k < nb; k++) {
     mtot[k] = v[k];
     ninv[k] = (uint64_t)v[nb + k];
@@ -631,18 +635,12 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write
     check_launch(c, "surf_project");
   }
   if (mtot) {
-    fetch(c, 0, nb, nb);
+    fetch_reduced(c, 0, nb, nb, NCCL_SUM);
     double m = 0.0;
     uint64_t n = 0;
     for (int b = 0; b < nb; b++) {
       m += c->h_out_d[b];
       n += c->h_out_u[b];
-    }
-    if (c->nranks > 1) {
-      double v[2] = {m, (double)n};
-      allreduce(c, v, 2, NCCL_SUM);
-      m = v[0];
-      n = (uint64_t)v[1];
     }
     *mtot = m;
     if (ninv) *ninv = n;
@@ -685,9 +683,8 @@ double op_alpha0(pms_ctx* c) {
     c->L->alpha0(c->stream, S.d, EL.d, c->structured ? nullptr : c->d_skip, c->N, c->Npad, c->R, 0);
     check_launch(c, "alpha0");
   }
-  fetch(c, 0, 1, 0);
+  fetch_reduced(c, 0, 1, 0, NCCL_MIN);
   double a = c->h_out_d[0];
-  allreduce(c, &a, 1, NCCL_MIN);
   if (a == DBL_MAX) a = 1.0;  // nothing moves: get_alpha_0_refmesh.hpp:164-165, Def.hpp:851-852
   if (!(a > 0.0)) throw PmsError(PMS_ERR_SMOOTHER, "bad alpha");
   return a;
@@ -705,9 +702,8 @@ void op_update(pms_ctx* c, double alpha, double* dmax, double* dmax_rel) {
   }
   X.version++;
   LG.version++;
-  fetch(c, 0, 2, 0);
+  fetch_reduced(c, 0, 2, 0, NCCL_MAX);
   double v[2] = {c->h_out_d[0], c->h_out_d[1]};
-  allreduce(c, v, 2, NCCL_MAX);
   *dmax = v[0];
   *dmax_rel = v[1];
 }
@@ -722,9 +718,8 @@ double op_snap_nodes(pms_ctx* c) {
     check_launch(c, "surf_snap");
   }
   X.version++;
-  fetch(c, 0, 1, 0);
+  fetch_reduced(c, 0, 1, 0, NCCL_MAX);
   double v[1] = {c->h_out_d[0]};
-  allreduce(c, v, 1, NCCL_MAX);
   return v[0];
 }
 
@@ -1007,9 +1002,8 @@ struct Driver {
         check_launch(c, "cg_r_dots");
       }
       Rr.version++;
-      fetch(c, 0, 3, 0);
+      fetch_reduced(c, 0, 3, 0, NCCL_SUM);
       double v[3] = {c->h_out_d[0], c->h_out_d[1], c->h_out_d[2]};
-      allreduce(c, v, 3, NCCL_SUM);
       st->dold = v[0];
       st->dmid = v[1];
       st->dnew = v[2];
