@@ -653,9 +653,10 @@ void op_edge_lengths(pms_ctx* c) {
   DField& W = c->field("coordinates_NM1");
   DField& EL = c->field("cg_edge_length");
   DField& NA = c->field("num_adj_elems");
+  if (!c->structured) ensure_eg(c);  // the gradient scratch doubles as the per-element edge-length buffer
   for (auto& mb : c->dev_blocks) {
-    Timed t(c, FAM_EDGE);
-    c->L->edge_lengths(c->stream, mb, W.d, c->Npad, EL.d, NA.d);
+    Timed t(c, FAM_EDGE, c->structured ? 1 : 2);
+    c->L->edge_lengths(c->stream, mb, W.d, c->Npad, EL.d, NA.d, c->structured ? nullptr : c->d_eg);
     check_launch(c, "edge_lengths");
   }
   if (c->structured) {

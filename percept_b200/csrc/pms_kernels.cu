@@ -1821,7 +1821,49 @@ __global__ void __launch_bounds__(NT) k_edge_csr(const MeshDev m, const double* 
   el[n] = nm / nele;
   na[n] = nele;
 }
-static void launch_edge_lengths(cudaStream_t st, const MeshDev& m, const double* w, long long stride, double* el, double* na) {
+// Two-pass form of k_edge_csr: the element's mean edge length does not depend on which node asks for it, so it is
+// computed once per element (instead of once per adjacent node: 8x the sqrt work and gathers for hexes) and the node
+// pass sums the stored values in the same CSR order - bit-identical result, 4.6 ms -> well under 1 ms at 256^3.
+template <int FL>
+__global__ void __launch_bounds__(NT) k_edge_elem(const MeshDev m, const double* __restrict__ w, const long long stride,
+                                                  double* __restrict__ scratch) {
+  const long long e = (long long)blockIdx.x * NT + threadIdx.x;
+  if (e >= m.nelems) return;
+  const int hex_edges[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6}, {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+  const int tet_edges[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
+  constexpr int NN = npe<FL>();
+  double v[8][3];
+#pragma unroll
+  for (int a = 0; a < NN; a++) {
+    const long long q = __ldg(&m.conn[(long long)a * m.conn_stride + e]);
+#pragma unroll
+    for (int d = 0; d < 3; d++) v[a][d] = __ldg(&w[d * stride + q]);
+  }
+  scratch[e] = (FL == FL_TET4) ? mean_edge_length<6>(v, tet_edges) : mean_edge_length<12>(v, hex_edges);
+}
+__global__ void __launch_bounds__(NT) k_edge_node(const MeshDev m, const double* __restrict__ scratch, double* __restrict__ el,
+                                                  double* __restrict__ na) {
+  const long long n = (long long)blockIdx.x * NT + threadIdx.x;
+  if (n >= m.nnodes) return;
+  double nm = 0.0, nele = 0.0;
+  for (long long p = m.csr_ptr[n]; p < m.csr_ptr[n + 1]; p++) {
+    nm += scratch[m.csr_ent[p] >> 3];
+    nele += 1.0;
+  }
+  el[n] = nm / nele;
+  na[n] = nele;
+}
+static void launch_edge_lengths(cudaStream_t st, const MeshDev& m, const double* w, long long stride, double* el, double* na,
+                                double* scratch) {
+  if (m.kind != KIND_SGRID && scratch) {
+    const unsigned ge = (unsigned)((m.nelems + NT - 1) / NT), gn = (unsigned)((m.nnodes + NT - 1) / NT);
+    if (m.kind == KIND_HEX8)
+      k_edge_elem<FL_HEX8><<<ge, NT, 0, st>>>(m, w, stride, scratch);
+    else
+      k_edge_elem<FL_TET4><<<ge, NT, 0, st>>>(m, w, stride, scratch);
+    k_edge_node<<<gn, NT, 0, st>>>(m, scratch, el, na);
+    return;
+  }
   if (m.kind == KIND_SGRID) {
     dim3 block(TBX, TBY, TBZ), grid((m.ni + TBX - 1) / TBX, (m.nj + TBY - 1) / TBY, (m.nk + TBZ - 1) / TBZ);
     k_edge_sgrid<<<grid, block, 0, st>>>(m, w, stride, el, na);

@@ -123,7 +123,8 @@ struct Launchers {
   void (*update)(cudaStream_t, double* x, double* lagged, const double* s, const double* edge, const uint8_t* fixed,
                  const uint8_t* owned, double alpha, long long n, long long stride, const Reduce&, int slot);
   // edge lengths: el = sum over adjacent elements of mean edge length, na = adjacency count (division done by divide())
-  void (*edge_lengths)(cudaStream_t, const MeshDev&, const double* w, long long stride, double* el, double* na);
+  // unstructured: `scratch` (>= nelems doubles, may be null) holds one mean edge length per element between the two passes
+  void (*edge_lengths)(cudaStream_t, const MeshDev&, const double* w, long long stride, double* el, double* na, double* scratch);
   void (*divide)(cudaStream_t, double* el, const double* na, long long n);
   // halo pack / unpack: buf[c*count + i] <-> f[c*stride + nodes[i]]
   void (*pack)(cudaStream_t, const double* f, long long stride, int ncomp, const int32_t* nodes, long long count, double* buf);
