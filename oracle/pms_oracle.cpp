@@ -10,6 +10,10 @@
 //   see tests/test_oracle_golden.py.  tet4 has no golden in the reference; it is
 //   cross-checked against central finite differences (the reference's own dormant
 //   check, ReferenceMeshSmootherConjugateGradientDef.hpp:1252-1335).
+//   PARITY UNPINNED (no golden vector, known-answer test or fixture in the reference's tests; pinned through properties
+//   instead, see the test files): the StructuredGridRefiner restatement (orc_refine_structured_*, tests/test_refine.py)
+//   and the smooth_surfaces hooks with analytic evaluators (orc_add_analytic_surface, orc_set_node_classification,
+//   orc_snap_nodes, orc_get_surface_normals; tests/test_surface_hooks.py - the reference evaluates third-party CAD).
 //
 // All file:line citations are relative to /root/reference/ ;
 //   SM/ = src/percept/mesh/mod/smoother/ , Def.hpp = SM/ReferenceMeshSmootherConjugateGradientDef.hpp
