@@ -1265,17 +1265,21 @@ static void launch_metric_multi1(cudaStream_t st, const MeshDev& m, int stage, c
 }
 static bool launch_metric_multi(cudaStream_t st, const MeshDev& m, int stage, int use_ref, int nb, const double* x, const double* s,
                                 const double* w, long long stride, const double* alphas, const Reduce& R, int slot) {
-  if (STRICT || m.kind == KIND_TET4 || (stage != 0 && !use_ref) || (nb != 8 && nb != 12)) return false;
+  if (STRICT || m.kind == KIND_TET4 || (stage != 0 && !use_ref) || (nb != 8 && nb != 12 && nb != 16)) return false;
   if (m.kind == KIND_SGRID) {
     if (nb == 8)
       launch_metric_multi1<FL_SGRID, 8>(st, m, stage, x, s, w, stride, alphas, R, slot);
-    else
+    else if (nb == 12)
       launch_metric_multi1<FL_SGRID, 12>(st, m, stage, x, s, w, stride, alphas, R, slot);
+    else
+      launch_metric_multi1<FL_SGRID, 16>(st, m, stage, x, s, w, stride, alphas, R, slot);
   } else {
     if (nb == 8)
       launch_metric_multi1<FL_HEX8, 8>(st, m, stage, x, s, w, stride, alphas, R, slot);
-    else
+    else if (nb == 12)
       launch_metric_multi1<FL_HEX8, 12>(st, m, stage, x, s, w, stride, alphas, R, slot);
+    else
+      launch_metric_multi1<FL_HEX8, 16>(st, m, stage, x, s, w, stride, alphas, R, slot);
   }
   return true;
 }

@@ -28,8 +28,8 @@ struct MeshDev {
   const int32_t* csr_ent32;        // same, 32-bit (when nelems*8 < 2^31): halves the gather's index traffic
 };
 
-constexpr int REDUCE_MAX_NV = 24;   // doubles one grid reduction can carry
-constexpr int MULTI_ALPHA_NB = 12;  // most trial step lengths per multi-alpha metric pass (kernels for 8 and 12)
+constexpr int REDUCE_MAX_NV = 32;   // doubles one grid reduction can carry
+constexpr int MULTI_ALPHA_NB = 16;  // most trial step lengths per multi-alpha metric pass (kernels for 8, 12 and 16)
 
 struct Reduce {  // scratch for deterministic two-level reductions (partials + last-block ticket)
   double* partial_d;            // [REDUCE_MAX_NV * max_blocks]
@@ -138,7 +138,7 @@ struct Launchers {
   // cross-rank interface sum (structured block per GPU), ascending rank order
   void (*shared_sum)(cudaStream_t, long long nshared, const int32_t* nodes, const int64_t* ptr, const int64_t* ent_pos,
                      const int32_t* ent_cnt, const double* recvbuf, double* f, int ncomp, long long stride);
-  // hex metric at nb (8 or 12) trial step lengths in one pass (line search speculation): out_d[slot + k] = metric at
+  // hex metric at nb (8, 12 or 16) trial step lengths in one pass (line search speculation): out_d[slot + k] = metric at
   // alphas[k], out_d[slot + nb + k] = number of invalid elements at alphas[k].  Returns false when not available
   // (tet4, strict build, ShapeB1 without reference mesh).
   bool (*metric_multi)(cudaStream_t, const MeshDev&, int stage, int use_ref, int nb, const double* x, const double* s,

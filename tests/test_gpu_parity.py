@@ -404,7 +404,7 @@ def test_multi_alpha_metric_matches_single_evaluations_and_oracle(kind, eps):
     for stage in (0, 1):
         before = g.launch_count()
         mg, ng = g.total_metric_multi(stage, alphas)
-        assert g.launch_count() - before == (2 if kind != "tet4" else len(alphas))  # 14 alphas = passes of 12 + 8
+        assert g.launch_count() - before == (1 if kind != "tet4" else len(alphas))  # 14 alphas = one pass of 16
         g.set_option("cache_metric", 0)
         for k, a in enumerate(alphas):
             mo, no = o.total_metric(stage, a)

@@ -19,11 +19,14 @@ for f, v in (("coordinates", X), ("coordinates_N", X), ("coordinates_NM1", W)):
     c.upload(f, v)
 st = c.state_init(); st.stage = 1
 niter = 6
+halv = []
 for it in range(niter):
+    h0 = st.n_line_search_halvings
     if it == 1:
         c.synchronize(); c.set_timing(1); c.kernel_time_reset(); t0 = time.time(); ev0 = (st.n_metric_evals, st.n_gradient_evals)
     st.iter = it; st.num_invalid = c.count_invalid_elements()
     m = c.run_one_iteration(st, 0.0)
+    halv.append(st.n_line_search_halvings - h0)
 c.synchronize(); wall = (time.time() - t0) / (niter - 1) * 1e3
 tot = 0
 for fam in ("metric", "gradient", "blas1", "update", "alpha0", "edge", "halo"):
@@ -33,5 +36,8 @@ print(f"kernels {tot/(niter-1):.3f} ms/iter, wall (timing on) {wall:.3f} ms/iter
 c.set_timing(0)
 t0 = time.time()
 for it in range(niter, niter + 5):
+    h0 = st.n_line_search_halvings
     st.iter = it; st.num_invalid = c.count_invalid_elements(); c.run_one_iteration(st, 0.0)
+    halv.append(st.n_line_search_halvings - h0)
 c.synchronize(); print(f"wall (timing off) {(time.time()-t0)/5*1e3:.3f} ms/iter")
+print("line-search halvings per iteration:", halv)
