@@ -5,7 +5,7 @@
  *   percept::ReferenceMeshSmootherConjugateGradientImpl<MeshType>
  *   (src/percept/mesh/mod/smoother/ReferenceMeshSmootherConjugateGradient.hpp:74-174)
  * whose members launch Kokkos functors.  The C++ host classes in
- * include/percept_b200/*.hpp keep that class API and call the entry points
+ * include/percept_b200/ (ReferenceMeshSmootherConjugateGradient.hpp) keep that class API and call the entry points
  * below; each entry point cites the reference member / functor it replaces.
  *
  * Conventions
