@@ -874,6 +874,19 @@ struct Driver {
     }
   }
 
+  bool sinfo_ok(bool need_g) const {
+    return c->sinfo.valid && c->sinfo.sv == c->field("cg_s").version && (!need_g || c->sinfo.gv == c->field("cg_g").version);
+  }
+  double alpha0_of_s() {
+    if (!sinfo_ok(false)) return op_alpha0(c);
+    double a = c->sinfo.alpha0;
+    if (a == DBL_MAX) a = 1.0;  // as op_alpha0
+    if (!(a > 0.0)) throw PmsError(PMS_ERR_SMOOTHER, "bad alpha");
+    return a;
+  }
+  double s_dot_g() { return sinfo_ok(true) ? c->sinfo.sg : op_dot(c, "cg_s", "cg_g"); }
+  double s_dot_s() { return sinfo_ok(false) ? c->sinfo.ss : op_dot(c, "cg_s", "cg_s"); }
+
   void s_equals_r() {  // copy_field(cg_s, cg_r)
     op_copy(c, "cg_s", "cg_r");
     halo_exchange(c, "cg_s");
@@ -884,13 +897,13 @@ struct Driver {
   double line_search(bool& restarted) {
     moved = false;
     const double alpha_fac = 10.0, tau = 0.5, c0 = 1.e-1, min_alpha_factor = 1.e-12;
-    st->alpha_0 = op_alpha0(c);
+    st->alpha_0 = alpha0_of_s();
     double alpha = alpha_fac * st->alpha_0;
     bool total_valid = false;
     uint64_t n_invalid = 0;
     const double metric_0 = tm(0.0, total_valid, &n_invalid);
     double metric = 0.0;
-    double sDotGrad = op_dot(c, "cg_s", "cg_g");
+    double sDotGrad = s_dot_g();
     if (sDotGrad >= 0.0) {
       s_equals_r();
       st->alpha_0 = op_alpha0(c);
@@ -1028,17 +1041,49 @@ struct Driver {
       DField& Rr = c->field("cg_r");
       DField& S = c->field("cg_s");
       DField& D = c->field("cg_d");
-      Timed t(c, FAM_BLAS1);
-      c->L->cg_s_update(c->stream, Rr.d, S.d, D.d, cg_beta, restart ? 1 : 0, c->N, c->Npad);
-      check_launch(c, "cg_s_update");
-      S.version++;
-      D.version++;
+      c->sinfo.valid = false;
+      if (c->cache_metric) {
+        // one pass: the update plus s.g, s.s and the alpha_0 scan the line search asks for next (bit-identical values)
+        DField& G = c->field("cg_g");
+        DField& EL = c->field("cg_edge_length");
+        {
+          Timed t(c, FAM_BLAS1);
+          c->L->cg_s_update_dots(c->stream, Rr.d, S.d, D.d, G.d, EL.d, c->dotmask_trivial ? nullptr : c->d_dotmask,
+                                 c->structured ? nullptr : c->d_skip, cg_beta, restart ? 1 : 0, c->N, c->Npad, c->R, 0);
+          check_launch(c, "cg_s_update_dots");
+        }
+        S.version++;
+        D.version++;
+        if (c->nranks > 1) {
+          Timed t(c, FAM_HALO);
+          PMS_NCCL(g_nccl.GroupStart());
+          PMS_NCCL(g_nccl.AllReduce(c->R.out_d, c->R.out_d, 2, NCCL_F64, NCCL_SUM, c->nccl_comm, c->stream));
+          PMS_NCCL(g_nccl.AllReduce(c->R.out_d + 2, c->R.out_d + 2, 1, NCCL_F64, NCCL_MIN, c->nccl_comm, c->stream));
+          PMS_NCCL(g_nccl.GroupEnd());
+        }
+        halo_exchange(c, "cg_s");
+        fetch(c, 0, 3, 0);
+        c->sinfo.valid = true;
+        c->sinfo.sv = S.version;
+        c->sinfo.gv = G.version;
+        c->sinfo.sg = c->h_out_d[0];
+        c->sinfo.ss = c->h_out_d[1];
+        c->sinfo.alpha0 = c->h_out_d[2];
+      } else {
+        {
+          Timed t(c, FAM_BLAS1);
+          c->L->cg_s_update(c->stream, Rr.d, S.d, D.d, cg_beta, restart ? 1 : 0, c->N, c->Npad);
+          check_launch(c, "cg_s_update");
+        }
+        S.version++;
+        D.version++;
+        halo_exchange(c, "cg_s");
+      }
     }
-    halo_exchange(c, "cg_s");
     bool restarted = false;
     const double alpha = line_search(restarted);
     st->restarted += restarted ? 1 : 0;
-    const double snorm = op_dot(c, "cg_s", "cg_s");
+    const double snorm = s_dot_s();
     st->grad_norm_scaled = st->alpha_0 * std::sqrt(snorm) / double(st->num_nodes);
     st->alpha = alpha;
     if (!moved) op_update(c, alpha, &st->dmax, &st->dmax_relative);  // update_node_positions, Def.hpp:395-410
@@ -1585,8 +1630,8 @@ int pms_commit(pms_ctx* c) {
   c->R.max_blocks = (int)maxb;
   c->R.partial_d = dalloc<double>((size_t)pmsk::REDUCE_MAX_NV * maxb);
   c->R.partial_u = dalloc<unsigned long long>((size_t)maxb);
-  c->R.ticket = dalloc<unsigned int>(1);
-  PMS_CUDA(cudaMemset(c->R.ticket, 0, sizeof(unsigned int)));
+  c->R.ticket = dalloc<unsigned int>(2);
+  PMS_CUDA(cudaMemset(c->R.ticket, 0, 2 * sizeof(unsigned int)));
   c->R.out_d = dalloc<double>(pms_ctx::NSLOT);
   c->R.out_u = dalloc<unsigned long long>(pms_ctx::NSLOT);
   PMS_CUDA(cudaMallocHost(&c->h_out_d, pms_ctx::NSLOT * sizeof(double)));

@@ -115,6 +115,12 @@ struct pms_ctx {
   bool pre_valid = false;
   uint64_t pre_xv = 0, pre_wv = 0, pre_gv = 0;
   int pre_stage = -1;
+  // what the line search asks about a freshly updated search direction, computed by the update kernel itself
+  struct SInfo {
+    bool valid = false;
+    uint64_t sv = 0, gv = 0;
+    double alpha0 = 0, sg = 0, ss = 0;
+  } sinfo;
   int spec_prev = 0;  // trial step lengths the previous line search visited (sizes the next speculative batch)
   bool speculate_line_search = true;  // evaluate the line search's alpha_init * tau^k trials in multi-alpha passes
   bool adj_fixed = false;

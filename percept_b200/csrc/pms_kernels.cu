@@ -1696,6 +1696,51 @@ static void launch_cg_s_update(cudaStream_t st, const double* r, double* s, doub
   k_cg_s_update<<<dim3(blas_blocks(n), 3), NT, 0, st>>>(r, s, d, beta, restart, n, stride);
 }
 
+// s update fused with s.g, s.s and the alpha_0 scan of the new s (one pass over the nodes instead of four)
+__global__ void __launch_bounds__(NT) k_cg_s_update_dots(const double* __restrict__ r, double* __restrict__ s, double* __restrict__ d,
+                                                         const double* __restrict__ g, const double* __restrict__ edge,
+                                                         const uint8_t* __restrict__ dotmask, const uint8_t* __restrict__ skip,
+                                                         const double beta, const int restart, const long long n,
+                                                         const long long stride, const Reduce R, const int slot) {
+  double acc[2] = {0.0, 0.0}, mn[1] = {DBL_MAX};
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    double sv[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const double rv = r[c * stride + i];
+      sv[c] = restart ? rv : 1.0 * rv + beta * s[c * stride + i];
+      s[c * stride + i] = sv[c];
+      d[c * stride + i] = rv;
+    }
+    if (!dotmask || dotmask[i]) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) acc[0] += sv[c] * g[c * stride + i];
+#pragma unroll
+      for (int c = 0; c < 3; c++) acc[1] += sv[c] * sv[c];
+    }
+    if (!(skip && skip[i])) {
+      double sn = 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) sn += sv[c] * sv[c];
+      sn = sqrt(sn);
+      if (sn > 0.0) {
+        const double cand = edge[i] / sn;
+        mn[0] = cand < mn[0] ? cand : mn[0];
+      }
+    }
+  }
+  grid_reduce<OpSum, 2, false>(acc, 0ull, R, slot);
+  Reduce R2 = R;  // second reduction of the same kernel: its own ticket and partial area
+  R2.ticket = R.ticket + 1;
+  R2.partial_d = R.partial_d + (size_t)2 * R.max_blocks;
+  grid_reduce<OpMin, 1, false>(mn, 0ull, R2, slot + 2);
+}
+static void launch_cg_s_update_dots(cudaStream_t st, const double* r, double* s, double* d, const double* g, const double* edge,
+                                    const uint8_t* dotmask, const uint8_t* skip, double beta, int restart, long long n,
+                                    long long stride, const Reduce& R, int slot) {
+  k_cg_s_update_dots<<<blas_blocks(n), NT, 0, st>>>(r, s, d, g, edge, dotmask, skip, beta, restart, n, stride, R, slot);
+}
+
 // alpha_0 candidates + min         (get_alpha_0_refmesh.hpp:168-193, Def.hpp:864-901)
 __global__ void __launch_bounds__(NT) k_alpha0(const double* __restrict__ s, const double* __restrict__ edge,
                                                const uint8_t* __restrict__ skip, const long long n, const long long stride,
@@ -2133,7 +2178,7 @@ static void launch_elem_fixed_bits(cudaStream_t st, const MeshDev& m, const uint
 
 static const Launchers g_launchers = {launch_metric,    launch_grad_elements, launch_grad_gather, launch_grad_fused_sgrid,
                                       launch_group_sum, launch_axpby,         launch_axpbypgz,    launch_set,
-                                      launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_alpha0,
+                                      launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_cg_s_update_dots, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,
                                       launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_shared_sum,
                                       launch_metric_multi, launch_refine_sgrid, launch_surf_project, launch_surf_snap, launch_surf_normals};

@@ -34,7 +34,7 @@ constexpr int MULTI_ALPHA_NB = 16;  // most trial step lengths per multi-alpha m
 struct Reduce {  // scratch for deterministic two-level reductions (partials + last-block ticket)
   double* partial_d;            // [REDUCE_MAX_NV * max_blocks]
   unsigned long long* partial_u;  // [max_blocks]
-  unsigned int* ticket;         // zero-initialised, self-resetting
+  unsigned int* ticket;         // [2] zero-initialised, self-resetting (the second one for a kernel's second reduction)
   double* out_d;                // result slots (device)
   unsigned long long* out_u;
   int max_blocks;
@@ -116,6 +116,12 @@ struct Launchers {
   // restart ? s = r : s = r + beta*s ; d = r   (Def.hpp:1057-1069 fused)
   void (*cg_s_update)(cudaStream_t, const double* r, double* s, double* d, double beta, int restart, long long n,
                       long long stride);
+  // the same update fused with what the line search asks next about the new s: out_d[slot] = s.g, out_d[slot+1] = s.s
+  // (both over `dotmask` nodes), out_d[slot+2] = min over non-`skip` nodes of edge/|s| (DBL_MAX if none).  Same
+  // per-thread accumulation order as dot / alpha0, hence bit-identical values.
+  void (*cg_s_update_dots)(cudaStream_t, const double* r, double* s, double* d, const double* g, const double* edge,
+                           const uint8_t* dotmask, const uint8_t* skip, double beta, int restart, long long n, long long stride,
+                           const Reduce&, int slot);
   // out_d[slot] = min over candidate nodes of edge/|s|, DBL_MAX if none (get_alpha_0_refmesh.hpp:168-193)
   void (*alpha0)(cudaStream_t, const double* s, const double* edge, const uint8_t* skip_mask, long long n, long long stride,
                  const Reduce&, int slot);
