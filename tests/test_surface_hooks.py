@@ -213,3 +213,24 @@ def test_gpu_surface_hook_errors():
         h.add_analytic_surface(7, (0, 0, 0))
     with pytest.raises(SmootherError, match="direction"):
         h.add_analytic_surface(0, (0, 0, 0, 0, 0, 0))
+
+
+def test_host_classifier_reproduces_the_box_classification():
+    """percept_b200.geometry.classify_nodes (set-up code): skin nodes on 1 / 2 / >=3 analytic surfaces are
+    surface / curve / vertex nodes - the classification the curved-box tests construct by hand."""
+    from percept_b200 import exodus, geometry
+    nele = 6
+    W, X, dof, surf = curved_box(nele)
+    surfaces = [{"kind": "plane", "point": [0, 0, 0], "normal": [-1, 0, 0]}, {"kind": "plane", "point": [1, 0, 0], "normal": [1, 0, 0]},
+                {"kind": "plane", "point": [0, 0, 0], "normal": [0, -1, 0]}, {"kind": "plane", "point": [0, 1, 0], "normal": [0, 2, 0]},
+                {"kind": "plane", "point": [0, 0, 0], "normal": [0, 0, -1]},
+                {"kind": "cylinder", "point": list(AXIS_P), "axis": list(AXIS_U), "radius": RAD}]
+    skin = exodus.skin_nodes(meshes.hex8_conn(nele), 8)
+    d2, s2 = geometry.classify_nodes(W, skin, surfaces, 1e-12)
+    assert np.array_equal(d2, dof) and np.array_equal(s2, surf)
+    kind, p = geometry.surface_params(surfaces[5])
+    assert kind == 2 and np.allclose(p, AXIS_P + AXIS_U + (RAD,))
+    # a skin node on no listed surface is held fixed
+    d3, _ = geometry.classify_nodes(W, skin, surfaces[:5], 1e-12)
+    top_interior = (surf == 5)
+    assert np.all(d3[top_interior] == 0)
