@@ -234,3 +234,46 @@ def test_host_classifier_reproduces_the_box_classification():
     d3, _ = geometry.classify_nodes(W, skin, surfaces[:5], 1e-12)
     top_interior = (surf == 5)
     assert np.all(d3[top_interior] == 0)
+
+
+@pytest.mark.gpu
+def test_smooth_cli_with_analytic_surfaces(tmp_path):
+    """`python -m percept_b200.smooth --smooth_surfaces=1 --surfaces geo.json`: the curved box written as Exodus; the
+    classifier finds faces / edges / corners from the geometry, face nodes slide and stay on their surface."""
+    import json
+    from scipy.io import netcdf_file
+    from percept_b200 import smooth
+    nele = 6
+    W, X, dof, surf = curved_box(nele)
+    conn = meshes.hex8_conn(nele)
+
+    def write(path, C):
+        nc = netcdf_file(path, "w", version=1)
+        nc.createDimension("num_nodes", C.shape[1])
+        nc.createDimension("num_el_in_blk1", conn.shape[0])
+        nc.createDimension("num_nod_per_el1", 8)
+        for i, n in enumerate(("coordx", "coordy", "coordz")):
+            v = nc.createVariable(n, "d", ("num_nodes",))
+            v[:] = C[i]
+        c = nc.createVariable("connect1", "i", ("num_el_in_blk1", "num_nod_per_el1"))
+        c[:] = conn + 1
+        nc.close()
+    # start from a mesh whose surface nodes already lie on the geometry (perturbed tangentially, then snapped by the oracle)
+    o, *_ = build(oracle, nele, 1, {"real_is_double": 1})
+    X0 = o.download("coordinates")
+    write(str(tmp_path / "x.e"), X0)
+    write(str(tmp_path / "w.e"), W)
+    geo = [{"kind": "plane", "point": [0, 0, 0], "normal": [-1, 0, 0]}, {"kind": "plane", "point": [1, 0, 0], "normal": [1, 0, 0]},
+           {"kind": "plane", "point": [0, 0, 0], "normal": [0, -1, 0]}, {"kind": "plane", "point": [0, 1, 0], "normal": [0, 1, 0]},
+           {"kind": "plane", "point": [0, 0, 0], "normal": [0, 0, -1]},
+           {"kind": "cylinder", "point": list(AXIS_P), "axis": list(AXIS_U), "radius": RAD}]
+    json.dump(geo, open(tmp_path / "geo.json", "w"))
+    smooth.main([str(tmp_path / "x.e"), str(tmp_path / "out.npz"), "--reference_mesh", str(tmp_path / "w.e"), "--smoother_niter", "12",
+                 "--smoother_tol", "1e-6", "--smooth_surfaces", "1", "--surfaces", str(tmp_path / "geo.json"), "--surface_tol", "1e-12",
+                 "--log", str(tmp_path / "log.txt")])
+    out = np.load(tmp_path / "out.npz")["coords"]
+    assert np.array_equal(out[:, dof < 2], W[:, dof < 2])
+    assert surface_residual(out, surf).max() <= 4e-15
+    assert np.abs(out[:, dof == 2] - X0[:, dof == 2]).max() > 1e-4
+    so = o.run_algorithm(12, 1e-6)
+    assert np.abs(out - o.download("coordinates")).max() <= 1e-9
