@@ -387,9 +387,9 @@ def run_ours(args):
                 "note": "the evaluation is FP64-pipe-bound (about 1400 FP64 instr/hex vs 64 lanes/clk/SM), see DESIGN.md; "
                         "fp64 pipe utilisation is in profiles/"}
     # the binding resource, stated beside the contract's HBM figure: FP64 thread-instructions of the evaluation
-    # (1338 per hex: 1410 by SASS count before the Gram-matrix form of the derivative took 9 per corner off) against the measured FP64 pipe rate of
+    # (1282 per hex: 1410 by SASS count before the Gram-matrix form of the derivative and the merged rsqrt took 16 per corner off) against the measured FP64 pipe rate of
     # this part (148 SMs x 64 lanes/clk, profiles/r01_fp64_peak.txt) at the SM clock sampled during the run
-    fp64_instr = 1338.0 * lm.nelems
+    fp64_instr = 1282.0 * lm.nelems
     fp64_peak = 148 * 64 * (clocks.get("sm_mhz") or 1965) * 1e6
     roofline["fp64_pipe"] = {"achieved_ginstr_s": fp64_instr / (kernel_ms_per_eval * 1e-3) / 1e9, "peak_ginstr_s": fp64_peak / 1e9,
                              "frac": fp64_instr / (kernel_ms_per_eval * 1e-3) / fp64_peak,

@@ -172,15 +172,24 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
       }
       const double y = (ys[0] + ys[1]) + ys[2];
       const double P = FAC_3SQRT3 * fabs(detW) * detA;
-      const double rr = fast_rsqrt(ok ? y * P * P : 1.0);
-      const double yr = y * rr;  // sqrt(y)/P
+      double yr, yrd = 0.0;  // sqrt(y)/P and, for the derivative, sqrt(y)/(P detA)
+      if (GRAD && PMS_GRAD_VIA_GRAM) {
+        // one rsqrt serves both: u = rsqrt(y (P detA)^2) = 1/(sqrt(y) P detA), y u = sqrt(y)/(P detA), times detA = sqrt(y)/P
+        // (saves the separate reciprocal of detA: 7 FP64 per corner)
+        const double Pd = P * detA;
+        yrd = y * fast_rsqrt(ok ? y * Pd * Pd : 1.0);
+        yr = yrd * detA;
+      } else {
+        yr = y * fast_rsqrt(ok ? y * P * P : 1.0);
+      }
       const double q = y * yr;   // y^1.5/P
       ((c & 1) ? val1 : val0) += ok ? q - detW : 0.0;
       if (GRAD) {
         cross3(a2, a0, K1);
         cross3(a0, a1, K2);
         const double k1 = ok ? 3.0 * yr : 0.0;
-        const double nk2 = ok ? -q * fast_rcp(detA) : 0.0;  // detA <= 0: corner contributes nothing (SmootherMetric.hpp:835)
+        // detA <= 0: corner contributes nothing (SmootherMetric.hpp:835)
+        const double nk2 = ok ? (PMS_GRAD_VIA_GRAM ? -y * yrd : -q * fast_rcp(detA)) : 0.0;
 #pragma unroll
         for (int r = 0; r < 3; r++) {
           const double (&t)[3] = Tp[r];
