@@ -394,7 +394,7 @@ def run_ours(args):
     roofline["fp64_pipe"] = {"achieved_ginstr_s": fp64_instr / (kernel_ms_per_eval * 1e-3) / 1e9, "peak_ginstr_s": fp64_peak / 1e9,
                              "frac": fp64_instr / (kernel_ms_per_eval * 1e-3) / fp64_peak,
                              "note": "whole evaluation incl. the HBM-bound gather pass (25 % of the time); the element pass alone "
-                                     "ran the FP64 pipe at 68.7 % in the ncu capture of profiles/r01_ncu_summary.txt"}
+                                     "ran the FP64 pipe at 71.0 % in the final ncu capture of profiles/r01_ncu_summary.txt"}
 
     # ---- CPU baseline on this box's host cores, bounded sample --------------------------------------------------
     try:
