@@ -241,3 +241,38 @@ def test_gpu_refiner_argument_errors():
     hexc.commit()
     with pytest.raises(SmootherError, match="structured"):
         hexc.refine_topology(pb.api.create())
+
+
+def test_oracle_refined_rotated_blocks_stay_connected():
+    """Non-identity zone-connectivity transform ((-2, 1, 3) / (2, -1, 3), ranges with reversed ends): the r -> 2r-1 map
+    of owner and donor ranges (StructuredGridRefiner.cpp:107-131) keeps the refined blocks consistently connected -
+    duplicates counted once, interface gradient equal to the refined single block."""
+    from tests.test_multiblock import build_two_blocks_rotated
+    nele = 4
+    X, W = meshes.perturbed_coords(nele, 0.3)
+    multi, maps = build_two_blocks_rotated(oracle, nele, X, W, {"real_is_double": 1})
+    single = meshes.build(oracle, "sgrid", nele, X, W, True, {"real_is_double": 1})
+    fm, nm = refine(oracle, multi, ("coordinates", "coordinates_NM1"))
+    fs, ns = refine(oracle, single, ("coordinates", "coordinates_NM1"))
+    nf = 2 * nele + 1
+    assert nm == ns == (2 * nele) ** 3 and fm.get_number_nodes() == fs.get_number_nodes() == nf ** 3
+    # fine index maps of the two blocks (block 1 stored with rotated local axes (a, b, c) = (j, m1 - (i - m), k))
+    m = nele // 2
+    m1 = nele - m
+    i0 = np.arange(0, 2 * m + 1)[None, None, :]
+    j0 = np.arange(nf)[None, :, None]
+    k0 = np.arange(nf)[:, None, None]
+    map0 = (i0 + nf * (j0 + nf * k0)).reshape(-1)
+    a = np.arange(nf)[None, None, :]
+    b = np.arange(2 * m1 + 1)[None, :, None]
+    c = np.arange(nf)[:, None, None]
+    map1 = ((2 * m + 2 * m1 - b) + nf * (a + nf * c)).reshape(-1)
+    fmaps = [map0, map1]
+    # (block 1 sums its face / cell averages in its own rotated axis order: equal to rounding, not bitwise)
+    assert np.max(np.abs(gather_single(fm, fmaps, "coordinates", 3, nf ** 3) - fs.download("coordinates"))) <= 4e-16
+    for stage in (0, 1):
+        ms, is_ = fs.metric_and_gradient(stage)
+        mm, im = fm.metric_and_gradient(stage)
+        assert im == is_ and abs(mm - ms) <= 1e-10 * max(abs(ms), 1e-300)
+        gs = fs.download("cg_g")
+        assert np.max(np.abs(gather_single(fm, fmaps, "cg_g", 3, nf ** 3) - gs)) <= 1e-12 * max(np.max(np.abs(gs)), 1e-300)
