@@ -230,7 +230,11 @@ long long find_root(std::vector<long long>& parent, long long a) {
 // ---------------------------------------------------------------------------------------------
 // operations shared by the C ABI and the CG driver
 // ---------------------------------------------------------------------------------------------
-void invalidate_cache(pms_ctx* c) { c->cache.clear(); }
+void invalidate_cache(pms_ctx* c) {  // options / masks changed: nothing evaluated earlier may be re-used
+  c->cache.clear();
+  c->pre_valid = false;
+  c->sinfo.valid = false;
+}
 
 void op_copy(pms_ctx* c, const char* dst, const char* src) {
   DField& d = c->field(dst);
