@@ -55,3 +55,19 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "liborc" not in txt and "orc_" not in txt and "oracle/" not in txt, f
+
+
+def test_reference_arm_of_the_bench_runs_without_a_gpu():
+    """`bench.py --impl reference` times the CPU restatement on the host cores and prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["unit"] == "Melem/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
