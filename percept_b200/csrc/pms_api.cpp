@@ -589,14 +589,23 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write
   // structured: get_gradient() never forwards m_use_ref_mesh to m_sgrid_gradient (Def.hpp:1485-1495) => always ref mesh
   const int use_ref = c->structured ? 1 : (c->use_ref_mesh ? 1 : 0);
   bool fused_ok = false;
-  if (c->structured) {
+  if (c->structured && c->sgrid_fused) {
+    if (!c->d_seam) {  // tile-seam scratch of the fused kernel, sized for the largest block (blocks run one after another)
+      size_t bytes = 0;
+      for (auto& mb : c->dev_blocks) bytes = std::max(bytes, c->L->sgrid_fused_scratch_bytes(mb));
+      c->d_seam = dalloc<double>(bytes / sizeof(double) + 1);
+    }
     fused_ok = true;
     for (int b = 0; b < nb && fused_ok; b++) {
-      Timed t(c, FAM_GRADIENT);
-      fused_ok = c->L->grad_fused_sgrid(c->stream, c->dev_blocks[b], stage, X.d, W.d, c->Npad, c->d_fixed, G.d, c->R, b);
+      Timed t(c, FAM_GRADIENT, 2);
+      fused_ok = c->L->grad_fused_sgrid(c->stream, c->dev_blocks[b], stage, X.d, W.d, c->Npad, c->d_fixed, G.d, c->R, b,
+                                        c->d_seam, c->keep_elem ? c->d_elem_metric : nullptr,
+                                        c->keep_elem ? c->d_elem_flag : nullptr);
+      check_launch(c, "grad_fused_sgrid");
       if (!fused_ok) {
-        c->launches--;
-        c->fam_launches[FAM_GRADIENT]--;
+        if (b > 0) throw PmsError(PMS_ERR_CUDA, "fused structured gradient refused a block after accepting another");
+        c->launches -= 2;
+        c->fam_launches[FAM_GRADIENT] -= 2;
       }
     }
   }
@@ -1171,9 +1180,11 @@ struct Driver {
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
+// every entry point runs on the context's own device (a process may hold contexts on several GPUs)
 #define PMS_TRY \
   if (!c) return PMS_ERR_ARG; \
-  try {
+  try {      \
+    if (c->stream) cudaSetDevice(c->device);
 #define PMS_CATCH                   \
   }                                 \
   catch (const PmsError& e) {       \
@@ -1223,7 +1234,7 @@ void pms_destroy(pms_ctx* c) {
                     c->d_csr_ptr,   c->d_csr_ent,   c->d_grp_ptr,    c->d_grp_nodes,  c->d_eg,       c->d_elem_metric,
                     c->d_elem_flag, c->R.partial_d, c->R.partial_u,  c->R.ticket,     c->R.out_d,    c->R.out_u,
                     c->d_send_nodes, c->d_recv_nodes, c->d_send_buf, c->d_recv_buf,   c->d_coll, c->d_skip, c->d_csr_ent32, c->d_if_nodes, c->d_sh_nodes, c->d_sh_cnt, c->d_sh_ptr, c->d_sh_pos,
-                    c->d_if_send, c->d_if_recv};
+                    c->d_if_send, c->d_if_recv, c->d_seam};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->h_out_d) cudaFreeHost(c->h_out_d);
@@ -1283,6 +1294,10 @@ int pms_set_option(pms_ctx* c, const char* key, double v) {
   } else if (k == "variant_grad_corners") {
     c->var_grad = (int)v;
     pms_fast::set_variant(c->var_metric, c->var_grad);
+    invalidate_cache(c);
+  } else if (k == "sgrid_fused") {  // 1 (default): one-pass tile kernel for structured gradients; 0: element pass + gather
+    c->sgrid_fused = v != 0;
+    invalidate_cache(c);
   } else
     throw PmsError(PMS_ERR_ARG, "unknown option " + k);
   PMS_CATCH

@@ -76,6 +76,8 @@ struct pms_ctx {
   int64_t *d_grp_ptr = nullptr, *d_grp_nodes = nullptr;
   long long n_groups = 0;
   double* d_eg = nullptr;  // element-gradient scratch [3*npe][Epad]
+  double* d_seam = nullptr;  // tile-seam scratch of the fused structured gradient (pms_sgrid_tile.cuh)
+  bool sgrid_fused = true;
   // brick tables of the scratch-free hex8 gradient (built lazily from the reference-mesh centroids)
   pmsk::BrickDev bricks{};
   bool bricks_built = false, bricks_failed = false;

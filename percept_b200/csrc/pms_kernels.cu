@@ -1573,10 +1573,7 @@ static void launch_grad_gather(cudaStream_t st, const MeshDev& m, const double* 
   }
 }
 
-static bool launch_grad_fused_sgrid(cudaStream_t, const MeshDev&, int, const double*, const double*, long long,
-                                    const uint8_t*, double*, const Reduce&, int) {
-  return false;  // not in this build: the two-pass element/gather path is used
-}
+#include "pms_sgrid_tile.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // multi-block interface reconciliation: complete sum over all duplicates, ascending block id
@@ -2177,6 +2174,7 @@ static void launch_elem_fixed_bits(cudaStream_t st, const MeshDev& m, const uint
 }
 
 static const Launchers g_launchers = {launch_metric,    launch_grad_elements, launch_grad_gather, launch_grad_fused_sgrid,
+                                      sgrid_fused_scratch_bytes,
                                       launch_group_sum, launch_axpby,         launch_axpbypgz,    launch_set,
                                       launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_cg_s_update_dots, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,

@@ -93,9 +93,13 @@ struct Launchers {
   // non-owned nodes.  r_out (may be null) receives a copy (cg_r = cg_g on STK meshes).
   void (*grad_gather)(cudaStream_t, const MeshDev&, const double* eg, long long eg_stride, const uint8_t* fixed,
                       const uint8_t* node_owned, double* g, double* r_out, long long stride);
-  // fused structured gradient (one kernel: cell tile in shared memory + node gather); returns false if unsupported
+  // fused structured metric + gradient (pms_sgrid_tile.cuh: cell tiles staged in shared memory, in-CTA node gather in the
+  // order of grad_gather, tile-seam nodes through `scratch` of sgrid_fused_scratch_bytes(block) bytes); returns false
+  // if unsupported for this block.  elem_metric / elem_flag optional.
   bool (*grad_fused_sgrid)(cudaStream_t, const MeshDev&, int stage, const double* x, const double* w, long long stride,
-                           const uint8_t* fixed, double* g, const Reduce&, int slot);
+                           const uint8_t* fixed, double* g, const Reduce&, int slot, double* scratch, double* elem_metric,
+                           int32_t* elem_flag);
+  size_t (*sgrid_fused_scratch_bytes)(const MeshDev&);
 
   // interface groups (multi-block structured): for group q, nodes grp_nodes[grp_ptr[q]..grp_ptr[q+1]) are duplicates of
   // one physical node, ascending block id.  val = sum over duplicates (in that order), written back to all.

@@ -19,6 +19,8 @@ def run(kind, nele, eps, reps=5):
     c.commit()
     c.upload("coordinates", X); c.upload("coordinates_N", X); c.upload("coordinates_NM1", W)
     c.set_option("cache_metric", 0)
+    if os.environ.get("QB_FUSED"):
+        c.set_option("sgrid_fused", int(os.environ["QB_FUSED"]))
     if os.environ.get("QB_VARIANT"):
         vm, vg = os.environ["QB_VARIANT"].split(",")
         c.set_option("variant_metric_corners", int(vm)); c.set_option("variant_grad_corners", int(vg))
