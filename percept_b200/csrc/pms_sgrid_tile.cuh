@@ -28,10 +28,16 @@
 // The same staging serves the metric-only kernels of the line search (k_sgrid_tile_metric).
 #pragma once
 
-constexpr int TL_X = 32, TL_Y = 8;  // threads of a CTA = cells of one sub-row step
+#ifndef TL_YDIM
+#define TL_YDIM 8
+#endif
 #ifndef TL_NSUB
 #define TL_NSUB 2
 #endif
+#ifndef TL_MINB
+#define TL_MINB 1
+#endif
+constexpr int TL_X = 32, TL_Y = TL_YDIM;  // threads of a CTA = cells of one sub-row step
 constexpr int TL_TY = TL_Y * TL_NSUB;            // cells per tile in j
 constexpr int TL_PX = TL_X + 1, TL_PY = TL_TY + 1;  // node patch of a tile
 constexpr int TL_ROWP = 36;                      // staged row: 18 x 16 B covering 33 nodes from an even node index
@@ -46,60 +52,129 @@ struct SeamDev {
   double* I;  // [lineI][slot 8][comp 3][nk][nj]  nodes with i on a tile line (j not on a tile line)
 };
 
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// one staged node plane: NARR*3 component planes of TL_PY rows of TL_ROWP doubles, then TL_PY rows of 64 mask bytes
+template <int NARR>
+struct TilePlane {
+  static constexpr int ROWS_D = NARR * 3 * TL_PY;
+  static constexpr int DOUBLES = ROWS_D * TL_ROWP + TL_PY * 8;
+};
+
+// Warp 0 stages node plane kp of the tile at (i0, j0): every node row is ONE bulk copy of the 16-byte-aligned span that
+// covers its 33 nodes (36 doubles from the even node index at or below the row's first node; 64 mask bytes from the
+// 16-byte boundary below it).  Every lane arms the plane's mbarrier with the bytes of its own rows (32 arrivals).
+template <int NARR>
+__device__ __forceinline__ void tl_stage_plane(double* buf, unsigned long long* bar, const MeshDev& m, const double* a0,
+                                               const double* a1, const double* a2, const uint8_t* fixed, const long long stride,
+                                               const int i0, const int j0, const int kp, const int lane) {
+  constexpr int NL = (TilePlane<NARR>::ROWS_D + TL_PY + 31) / 32;
+  const void* src[NL];
+  unsigned dst[NL], nb[NL], total = 0;
+  const int rows = min(TL_PY, m.nj - j0);
+#pragma unroll
+  for (int it = 0; it < NL; it++) {
+    const int line = lane + 32 * it;
+    const int ac = line / TL_PY, row = line % TL_PY;  // ac = array * 3 + component; ac == NARR*3: the fixed mask
+    nb[it] = 0;
+    src[it] = nullptr;
+    dst[it] = 0;
+    if (kp < m.nk && ac <= NARR * 3 && row < rows) {
+      const long long nrow = m.node_off + i0 + (long long)m.ni * ((j0 + row) + (long long)m.nj * kp);
+      if (ac < NARR * 3) {
+        const long long a = nrow & ~1LL;
+        const long long n = stride - a < TL_ROWP ? stride - a : TL_ROWP;
+        const double* base = ac < 3 ? a0 : (ac < 6 ? a1 : a2);
+        src[it] = base + (ac % 3) * stride + a;
+        dst[it] = smem_u32(buf + (ac * TL_PY + row) * TL_ROWP);
+        nb[it] = (unsigned)n * 8u;
+      } else {
+        const long long a = nrow & ~15LL;
+        const long long n = stride - a < 64 ? stride - a : 64;
+        src[it] = fixed + a;
+        dst[it] = smem_u32(buf + TilePlane<NARR>::ROWS_D * TL_ROWP + row * 8);
+        nb[it] = (unsigned)n;
+      }
+      total += nb[it];
+    }
+  }
+  mbar_arrive_expect_tx(bar, total);
+#pragma unroll
+  for (int it = 0; it < NL; it++)
+    if (nb[it])
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst[it]),
+                   "l"(src[it]), "r"(nb[it]), "r"(smem_u32(bar))
+                   : "memory");
+}
 
 // vertices of one cell read in place from two staged planes: V(p, r), p = di + 2 dj + 4 dk
-template <int NARR>
 struct TileVerts {
   const double* pl[2];  // plane k / k+1, already offset to this array's component 0
   int o[2][2];          // [dk][dj]: row * TL_ROWP + column of the cell's (di = 0) node
   PMS_DI double operator()(int p, int r) const { return pl[p >> 2][r * (TL_PY * TL_ROWP) + o[p >> 2][(p >> 1) & 1] + (p & 1)]; }
 };
 
-// stage node plane kp of NARR 3-component arrays (a0, a1[, a2]; component c at + c * stride) for the tile at (i0, j0)
-template <int NARR>
-__device__ __forceinline__ void tl_issue_plane(double* buf, const MeshDev& m, const double* a0, const double* a1,
-                                               const double* a2, const long long stride, const int i0, const int j0,
-                                               const int kp) {
-  if (kp < m.nk) {
-    const int rows = min(TL_PY, m.nj - j0);
-    const int total = NARR * 3 * rows * (TL_ROWP / 2);
-    for (int q = threadIdx.x + TL_X * threadIdx.y; q < total; q += TL_NTH) {
-      const int ch = q % (TL_ROWP / 2);
-      const int t = q / (TL_ROWP / 2);
-      const int row = t % rows, ac = t / rows;  // ac = array * 3 + component
-      const long long nrow = m.node_off + i0 + (long long)m.ni * ((j0 + row) + (long long)m.nj * kp);
-      const long long a = (nrow & ~1LL) + 2 * ch;
-      const double* src = ac < 3 ? a0 : (ac < 6 ? a1 : a2);
-      if (a + 2 <= stride) cp_async16(buf + (ac * TL_PY + row) * TL_ROWP + 2 * ch, src + (ac % 3) * stride + a);
-    }
+// node slots of a thread: round r < TL_NSUB -> patch node (tx, ty + 8 r); round TL_NSUB -> row TL_TY (ty == 0) and the
+// column pi = TL_X (ty == 1, pj = tx)
+__device__ __forceinline__ bool tl_slot_node(const int r, const int tx, const int ty, int& pi, int& pj) {
+  if (r < TL_NSUB) {
+    pi = tx;
+    pj = ty + TL_Y * r;
+    return true;
   }
-  cp_async_commit();
-}
-
-// parity of the first staged element of a node row (the row is staged from the even index at or below its first node)
-__device__ __forceinline__ int tl_row_off(const MeshDev& m, const int i0, const int j, const int k) {
-  return (int)((m.node_off + i0 + (long long)m.ni * (j + (long long)m.nj * k)) & 1LL);
+  if (ty == 0) {
+    pi = tx;
+    pj = TL_TY;
+    return true;
+  }
+  pi = TL_X;
+  pj = tx;
+  return ty == 1 && tx < TL_PY;
 }
 
 template <int STAGE>
-__global__ void __launch_bounds__(TL_NTH, 1) k_sgrid_tile_grad(const MeshDev m, const double* __restrict__ x,
+__global__ void __launch_bounds__(TL_NTH, TL_MINB) k_sgrid_tile_grad(const MeshDev m, const double* __restrict__ x,
                                                                const double* __restrict__ w, const long long stride,
                                                                const uint8_t* __restrict__ fixed, double* __restrict__ g,
                                                                const SeamDev seam, const int ntx, const int nty, const int kc,
                                                                const Reduce R, const int slot, double* __restrict__ em,
                                                                int32_t* __restrict__ ef) {
   extern __shared__ double sm[];
-  constexpr int PLANE = 6 * TL_PY * TL_ROWP;
-  double* const planes = sm;                    // [3][PLANE]
-  double* const ex = sm + 3 * PLANE;            // [24][TL_NCELL]
-  double* const carry = ex + 24 * TL_NCELL;     // [3][TL_NNODE]
-  int* const info = reinterpret_cast<int*>(carry + 3 * TL_NNODE);  // [TL_NNODE]
+  constexpr int PLANE = TilePlane<2>::DOUBLES;
+  constexpr int NSLOT = (TL_NSUB + 1) * TL_NTH;
+  double* const planes = sm;                 // [3][PLANE]
+  double* const ex = sm + 3 * PLANE;         // [24][TL_NCELL]
+  double* const carry = ex + 24 * TL_NCELL;  // [3][NSLOT]
+  int* const info = reinterpret_cast<int*>(carry + 3 * NSLOT);                             // [NSLOT]
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(info + NSLOT);    // [3]
+  double* const cellm = reinterpret_cast<double*>(bars + 4);                               // [TL_NCELL] metric of the layer's cells
+  int* const rowctr = reinterpret_cast<int*>(cellm + TL_NCELL);                            // [2] next cell row to evaluate
+  uint8_t* const cellv = reinterpret_cast<uint8_t*>(rowctr + 2);                           // [TL_NCELL] 1 = valid
   const int tx = threadIdx.x, ty = threadIdx.y, tid = tx + TL_X * ty;
   const int tile = blockIdx.x % (ntx * nty), chunk = blockIdx.x / (ntx * nty);
   const int i0 = (tile % ntx) * TL_X, j0 = (tile / ntx) * TL_TY;
@@ -108,48 +183,72 @@ __global__ void __launch_bounds__(TL_NTH, 1) k_sgrid_tile_grad(const MeshDev m, 
   const int kb = chunk * kc, ke = min(kb + kc, nck);
   const int kstart = kb > 0 ? kb - 1 : 0;  // one warm-up layer below the chunk builds the carry
 
-  // per patch node: bit0 exists, bit1 seam (bit2: the j line, else the i line), bits 4..7 adjacent tile cells (dj*2+di)
-  for (int q = tid; q < TL_NNODE; q += TL_NTH) {
-    const int pi = q % TL_PX, pj = q / TL_PX;
-    const int i = i0 + pi, j = j0 + pj;
-    int f = 0;
-    if (i < m.ni && j < m.nj) {
-      f = 1;
-      const bool sj = (j % TL_TY == 0) && j > 0 && j < m.nj - 1, si = (i % TL_X == 0) && i > 0 && i < m.ni - 1;
-      if (sj) f |= 2 | 4;
-      else if (si) f |= 2;
+  if (tid == 0) {
+    rowctr[0] = rowctr[1] = 0;
 #pragma unroll
-      for (int c4 = 0; c4 < 4; c4++) {
-        const int cx = pi - 1 + (c4 & 1), cy = pj - 1 + (c4 >> 1);
-        if (cx >= 0 && cx < actx && cy >= 0 && cy < acty) f |= 16 << c4;
+    for (int b = 0; b < 3; b++) mbar_init(&bars[b], 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // per node slot: bit0 exists, bit1 seam (bit2: on a j line, else on an i line), bits 4..7 adjacent tile cells (dj*2+di)
+#pragma unroll
+  for (int r = 0; r <= TL_NSUB; r++) {
+    int pi, pj, f = 0;
+    if (tl_slot_node(r, tx, ty, pi, pj)) {
+      const int i = i0 + pi, j = j0 + pj;
+      if (i < m.ni && j < m.nj) {
+        f = 1;
+        const bool sj = (j % TL_TY == 0) && j > 0 && j < m.nj - 1, si = (i % TL_X == 0) && i > 0 && i < m.ni - 1;
+        if (sj)
+          f |= 2 | 4;
+        else if (si)
+          f |= 2;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+          const int cx = pi - 1 + (c4 & 1), cy = pj - 1 + (c4 >> 1);
+          if (cx >= 0 && cx < actx && cy >= 0 && cy < acty) f |= 16 << c4;
+        }
       }
     }
+    const int q = r * TL_NTH + tid;
     info[q] = f;
     carry[q] = 0.0;
-    carry[TL_NNODE + q] = 0.0;
-    carry[2 * TL_NNODE + q] = 0.0;
+    carry[NSLOT + q] = 0.0;
+    carry[2 * NSLOT + q] = 0.0;
   }
-
-  tl_issue_plane<2>(planes + (kstart % 3) * PLANE, m, x, w, nullptr, stride, i0, j0, kstart);
-  tl_issue_plane<2>(planes + ((kstart + 1) % 3) * PLANE, m, x, w, nullptr, stride, i0, j0, kstart + 1);
+  __syncthreads();
+  if (ty == 0) {
+    tl_stage_plane<2>(planes + (kstart % 3) * PLANE, &bars[kstart % 3], m, x, w, nullptr, fixed, stride, i0, j0, kstart, tx);
+    tl_stage_plane<2>(planes + ((kstart + 1) % 3) * PLANE, &bars[(kstart + 1) % 3], m, x, w, nullptr, fixed, stride, i0, j0,
+                      kstart + 1, tx);
+  }
+  mbar_wait(&bars[kstart % 3], 0);
 
   double val[1] = {0.0};
   unsigned long long inv = 0;
   const long long plane_nodes = (long long)m.ni * m.nj;
+  const int par0 = (int)((m.node_off + i0) & 1LL), pni = m.ni & 1, pnj = m.nj & 1;
 
   for (int k = kstart; k < ke; k++) {
     const bool warm = k < kb;
-    cp_async_wait<0>();
-    __syncthreads();  // plane k+1 landed for everyone; ex, carry and the buffer of plane k-1 are free
-    tl_issue_plane<2>(planes + ((k + 2) % 3) * PLANE, m, x, w, nullptr, stride, i0, j0, k + 2);
+    __syncthreads();  // everyone is done with layer k-1: ex, carry and the buffer of plane k-1 are free
+    if (ty == 0)
+      tl_stage_plane<2>(planes + ((k + 2) % 3) * PLANE, &bars[(k + 2) % 3], m, x, w, nullptr, fixed, stride, i0, j0, k + 2, tx);
+    mbar_wait(&bars[(k + 1) % 3], (unsigned)(((k + 1 - kstart) / 3) & 1));
     const double* const p0 = planes + (k % 3) * PLANE;
     const double* const p1 = planes + ((k + 1) % 3) * PLANE;
 
+    // Cell rows are handed out dynamically (one row of 32 cells per request): with two warps per scheduler and a
+    // barrier per layer, a static split leaves the faster warp of each pair idle at the barrier for ~17 % of the time.
+    // Values do not depend on which warp evaluates a row; the metric is summed later by a fixed thread per cell.
+    if (tid == 0) rowctr[(k + 1) & 1] = 0;
 #pragma unroll 1
-    for (int sub = 0; sub < TL_NSUB; sub++) {
-      const int cj = ty + TL_Y * sub;
-      if (tx >= actx || cj >= acty) continue;
-      TileVerts<2> VC, VO;
+    for (;;) {
+      int cj = 0;
+      if (tx == 0) cj = atomicAdd(&rowctr[k & 1], 1);
+      cj = __shfl_sync(0xffffffffu, cj, 0);
+      if (cj >= acty) break;
+      if (tx >= actx) continue;
+      TileVerts VC, VO;
       VC.pl[0] = p0;
       VC.pl[1] = p1;
       VO.pl[0] = p0 + 3 * TL_PY * TL_ROWP;
@@ -158,7 +257,9 @@ __global__ void __launch_bounds__(TL_NTH, 1) k_sgrid_tile_grad(const MeshDev m, 
       for (int dk = 0; dk < 2; dk++)
 #pragma unroll
         for (int dj = 0; dj < 2; dj++) {
-          const int o = (cj + dj) * TL_ROWP + tx + tl_row_off(m, i0, j0 + cj + dj, k + dk);
+          // parity of the row's first node: the row is staged from the even node index at or below it
+          const int par = (par0 + pni * ((j0 + cj + dj + pnj * (k + dk)) & 1)) & 1;
+          const int o = (cj + dj) * TL_ROWP + tx + par;
           VC.o[dk][dj] = o;
           VO.o[dk][dj] = o;
         }
@@ -183,38 +284,44 @@ __global__ void __launch_bounds__(TL_NTH, 1) k_sgrid_tile_grad(const MeshDev m, 
       for (int a = 0; a < 8; a++)
 #pragma unroll
         for (int r = 0; r < 3; r++) ex[(a * 3 + r) * TL_NCELL + cell] = use ? grad[a][r] : 0.0;
-      if (!warm) {
-        val[0] += mm;
-        inv += valid ? 0 : 1;
-        if (em || ef) {
-          const long long e = m.elem_off + (i0 + tx) + (long long)nci * ((j0 + cj) + (long long)ncj * k);
-          if (em) em[e] = mm;
-          if (ef) ef[e] = valid ? 0 : 1;
-        }
+      cellm[cell] = mm;
+      cellv[cell] = valid ? 1 : 0;
+      if (!warm && (em || ef)) {
+        const long long e = m.elem_off + (i0 + tx) + (long long)nci * ((j0 + cj) + (long long)ncj * k);
+        if (em) em[e] = mm;
+        if (ef) ef[e] = valid ? 0 : 1;
       }
     }
     __syncthreads();
 
     // node phase: plane k is completed by the bottom contributions of layer k, the top ones start plane k+1
-    for (int q = tid; q < TL_NNODE; q += TL_NTH) {
+    const long long nbase = m.node_off + i0 + (long long)m.ni * j0 + plane_nodes * k;
+    const uint8_t* const fx_rows = reinterpret_cast<const uint8_t*>(p0 + TilePlane<2>::ROWS_D * TL_ROWP);
+#pragma unroll
+    for (int r = 0; r <= TL_NSUB; r++) {
+      const int q = r * TL_NTH + tid;
+      if (r < TL_NSUB && !warm && tx < actx && ty + TL_Y * r < acty) {  // total_element_metric.cpp:271-307
+        val[0] += cellm[(ty + TL_Y * r) * TL_X + tx];
+        inv += cellv[(ty + TL_Y * r) * TL_X + tx] ? 0 : 1;
+      }
       const int f = info[q];
       if (!(f & 1)) continue;
-      const int pi = q % TL_PX, pj = q / TL_PX;
-      const int i = i0 + pi, j = j0 + pj;
+      int pi, pj;
+      tl_slot_node(r, tx, ty, pi, pj);
+      const double* const exn = ex + (pj - 1) * TL_X + (pi - 1);  // cell (dj, di) of this node at + dj * TL_X + di
       if (f & 2) {
         if (warm) continue;
         // seam node: individual contributions, slot = dk*4 + dj*2 + di around the node
+        const int i = i0 + pi, j = j0 + pj;
         double* base;
         long long pstride, pos0;
         if (f & 4) {
-          const int line = j / TL_TY - 1;
           pstride = (long long)m.nk * m.ni;
-          base = seam.J + (long long)line * 24 * pstride;
+          base = seam.J + (long long)(j / TL_TY - 1) * 24 * pstride;
           pos0 = (long long)k * m.ni + i;
         } else {
-          const int line = i / TL_X - 1;
           pstride = (long long)m.nk * m.nj;
-          base = seam.I + (long long)line * 24 * pstride;
+          base = seam.I + (long long)(i / TL_X - 1) * 24 * pstride;
           pos0 = (long long)k * m.nj + j;
         }
         const long long pos1 = pos0 + ((f & 4) ? m.ni : m.nj);  // the same node of plane k+1
@@ -222,59 +329,348 @@ __global__ void __launch_bounds__(TL_NTH, 1) k_sgrid_tile_grad(const MeshDev m, 
         for (int c4 = 0; c4 < 4; c4++) {
           if (!(f & (16 << c4))) continue;
           const int di = c4 & 1, dj = c4 >> 1;
-          const int cell = (pj - 1 + dj) * TL_X + (pi - 1 + di);
           const int a = (1 - di) + 2 * (1 - dj);
 #pragma unroll
-          for (int r = 0; r < 3; r++) {
-            base[((4 + c4) * 3 + r) * pstride + pos0] = ex[(a * 3 + r) * TL_NCELL + cell];        // dk = 1 cell of plane k
-            base[(c4 * 3 + r) * pstride + pos1] = ex[((a + 4) * 3 + r) * TL_NCELL + cell];        // dk = 0 cell of plane k+1
+          for (int rr = 0; rr < 3; rr++) {
+            base[((4 + c4) * 3 + rr) * pstride + pos0] = exn[(a * 3 + rr) * TL_NCELL + dj * TL_X + di];       // dk = 1 cell of plane k
+            base[(c4 * 3 + rr) * pstride + pos1] = exn[((a + 4) * 3 + rr) * TL_NCELL + dj * TL_X + di];       // dk = 0 cell of plane k+1
           }
         }
         continue;
       }
       double acc[3], top[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-      for (int r = 0; r < 3; r++) acc[r] = carry[r * TL_NNODE + q];
+      for (int rr = 0; rr < 3; rr++) acc[rr] = carry[rr * NSLOT + q];
 #pragma unroll
       for (int c4 = 0; c4 < 4; c4++) {
         if (!(f & (16 << c4))) continue;
         const int di = c4 & 1, dj = c4 >> 1;
-        const int cell = (pj - 1 + dj) * TL_X + (pi - 1 + di);
         const int a = (1 - di) + 2 * (1 - dj);  // this node's local index in that cell (bottom face)
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-          acc[r] += ex[(a * 3 + r) * TL_NCELL + cell];
-          top[r] += ex[((a + 4) * 3 + r) * TL_NCELL + cell];
+        for (int rr = 0; rr < 3; rr++) {
+          acc[rr] += exn[(a * 3 + rr) * TL_NCELL + dj * TL_X + di];
+          top[rr] += exn[((a + 4) * 3 + rr) * TL_NCELL + dj * TL_X + di];
         }
       }
 #pragma unroll
-      for (int r = 0; r < 3; r++) carry[r * TL_NNODE + q] = top[r];
+      for (int rr = 0; rr < 3; rr++) carry[rr * NSLOT + q] = top[rr];
       if (!warm) {
-        const long long n = m.node_off + i + (long long)m.ni * j + plane_nodes * k;
-        const bool fx = fixed[n] != 0;  // fixup: gradient_functors.hpp:223-243
+        const long long n = nbase + (long long)m.ni * pj + pi;
+        const bool fx = fx_rows[pj * 64 + (int)((nbase + (long long)m.ni * pj) & 15LL) + pi] != 0;  // fixup: gradient_functors.hpp:223-243
 #pragma unroll
-        for (int r = 0; r < 3; r++) g[r * stride + n] = fx ? 0.0 : acc[r];
+        for (int rr = 0; rr < 3; rr++) g[rr * stride + n] = fx ? 0.0 : acc[rr];
       }
     }
     // (the __syncthreads at the top of the next layer orders this phase before ex / carry are written again)
   }
-  cp_async_wait<0>();
   if (ke == nck) {  // top plane of the block: only the cells below it exist
     __syncthreads();
-    for (int q = tid; q < TL_NNODE; q += TL_NTH) {
+    const long long nbase = m.node_off + i0 + (long long)m.ni * j0 + plane_nodes * nck;
+#pragma unroll
+    for (int r = 0; r <= TL_NSUB; r++) {
+      const int q = r * TL_NTH + tid;
       const int f = info[q];
       if (!(f & 1) || (f & 2)) continue;
-      const int pi = q % TL_PX, pj = q / TL_PX;
-      const long long n = m.node_off + (i0 + pi) + (long long)m.ni * (j0 + pj) + plane_nodes * nck;
+      int pi, pj;
+      tl_slot_node(r, tx, ty, pi, pj);
+      const long long n = nbase + (long long)m.ni * pj + pi;
       const bool fx = fixed[n] != 0;
 #pragma unroll
-      for (int r = 0; r < 3; r++) g[r * stride + n] = fx ? 0.0 : carry[r * TL_NNODE + q];
+      for (int rr = 0; rr < 3; rr++) g[rr * stride + n] = fx ? 0.0 : carry[rr * NSLOT + q];
     }
   }
+  // the last staged planes (k+1 of the last layer and k+2) must have landed before the CTA may exit
+  mbar_wait(&bars[(ke + 1) % 3], (unsigned)(((ke + 1 - kstart) / 3) & 1));
   grid_reduce<OpSum, 1, true>(val, inv, R, slot);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-specialised form (the one the launcher uses).  The kernel above alternates, per layer, an FP64-bound cell phase
+// and a latency-bound node phase separated by CTA barriers: ncu showed the FP64 pipe idle for 30 % of the time (node
+// phase 13 %, warps waiting at the barrier for the slower warp of their scheduler pair 17 %).  Here
+//   * 8 compute warps (setmaxnreg 232) evaluate one cell per thread per layer and write its 24 contributions to one of
+//     TWO exchange buffers; they never execute a CTA barrier,
+//   * 4 helper warps (setmaxnreg 40): warp 8 stages the node planes with TMA bulk copies two planes ahead; all four run
+//     the node phase of layer k (ordered gather, carry, stores, seam scratch) while the compute warps are in layer k+1.
+// Hand-off through mbarriers: pfull[3] (TMA complete_tx), pempty[3] (everyone done with a plane buffer),
+// xfull[2] / xempty[2] (exchange buffer written / gathered).  Tile = 32 x 8 cells, one cell per compute thread.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int WS_TY = 8;                                  // cell rows of a tile
+constexpr int WS_PY = WS_TY + 1;                          // node rows of its patch
+constexpr int WS_NC = 256, WS_NH = 128;                   // compute / helper threads
+constexpr int WS_NNODE = TL_PX * WS_PY;                   // 297
+constexpr int WS_NRND = (WS_NNODE + WS_NH - 1) / WS_NH;   // node rounds per helper thread (3)
+constexpr int WS_NPL = 4;                                 // staged plane buffers (planes k, k+1 in use, k+2, k+3 in flight)
+constexpr int WS_PLANE = 6 * WS_PY * TL_ROWP;             // doubles per staged plane
+// exchange buffer: per (local node a, component r) a grid of (WS_TY + 2) x (TL_X + 2) cells with a zero border, so the
+// node phase reads the four cells around a node unconditionally (+0.0 does not change a sum that started at +0.0)
+constexpr int WS_EXP = TL_X + 2;
+constexpr int WS_EXPL = (WS_TY + 2) * WS_EXP;
+constexpr int WS_EX = 24 * WS_EXPL;
+// 256 x 232 + 128 x 40 = 64512 = the 384 x 168 registers the CTA is launched with (setmaxnreg.inc blocks for ever when the
+// pool cannot supply the increase)
+constexpr int WS_REG_C = 232, WS_REG_H = 40;
+constexpr size_t WS_SMEM = (size_t)(WS_NPL * WS_PLANE + 2 * WS_EX + 3 * WS_NNODE + 1) * sizeof(double) + 16 * 8 +
+                           WS_NRND * WS_NH * sizeof(int);
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// The helper threads stage node plane kp (x, w: 3 components each) into buf, completing on bar (WS_NH arrivals): every
+// node row is ONE bulk copy of the 16-byte-aligned span covering its 33 nodes (36 doubles from the even node index at
+// or below the row's first node).  Helper thread h < 54 issues row h.
+__device__ __forceinline__ void ws_stage_plane(double* buf, unsigned long long* bar, const MeshDev& m, const double* x,
+                                               const double* w, const long long stride, const int i0, const int j0,
+                                               const int kp, const int h) {
+  const int ac = h / WS_PY, row = h % WS_PY;  // ac = array * 3 + component
+  const int rows = min(WS_PY, m.nj - j0);
+  if (kp < m.nk && ac < 6 && row < rows) {
+    const long long nrow = m.node_off + i0 + (long long)m.ni * ((j0 + row) + (long long)m.nj * kp);
+    const long long a = nrow & ~1LL;
+    const long long n = stride - a < TL_ROWP ? stride - a : TL_ROWP;
+    const unsigned nb = (unsigned)n * 8u;
+    mbar_arrive_expect_tx(bar, nb);
+    bulk_g2s(buf + (ac * WS_PY + row) * TL_ROWP, (ac < 3 ? x : w) + (ac % 3) * stride + a, nb, bar);
+  } else {
+    mbar_arrive(bar);
+  }
+}
+
+struct WsVerts {  // vertices of one cell read in place from two staged planes: V(p, r), p = di + 2 dj + 4 dk
+  const double* pl[2];
+  int o[2][2];
+  PMS_DI double operator()(int p, int r) const { return pl[p >> 2][r * (WS_PY * TL_ROWP) + o[p >> 2][(p >> 1) & 1] + (p & 1)]; }
+};
+
+template <int STAGE>
+__global__ void __launch_bounds__(WS_NC + WS_NH, 1) k_sgrid_tile_ws(const MeshDev m, const double* __restrict__ x,
+                                                                    const double* __restrict__ w, const long long stride,
+                                                                    const uint8_t* __restrict__ fixed, double* __restrict__ g,
+                                                                    const SeamDev seam, const int ntx, const int nty,
+                                                                    const int kc, const Reduce R, const int slot,
+                                                                    double* __restrict__ em, int32_t* __restrict__ ef) {
+  extern __shared__ double sm[];
+  double* const planes = sm;                        // [WS_NPL][WS_PLANE]
+  double* const ex = sm + WS_NPL * WS_PLANE;        // [2][24][WS_EXPL]
+  double* const carry = ex + 2 * WS_EX;             // [3][WS_NNODE]
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(carry + 3 * WS_NNODE + 1);
+  unsigned long long* const pfull = bars;                 // [WS_NPL] TMA complete_tx: the plane has landed
+  unsigned long long* const pempty = bars + WS_NPL;       // [WS_NPL] every compute thread is done with the plane
+  unsigned long long* const xfull = bars + 2 * WS_NPL;    // [2] the layer's contributions are in the exchange buffer
+  unsigned long long* const xempty = xfull + 2;           // [2] ... and have been gathered
+  int* const ninfo = reinterpret_cast<int*>(bars + 16);   // [WS_NRND * WS_NH]
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x % (ntx * nty), chunk = blockIdx.x / (ntx * nty);
+  const int i0 = (tile % ntx) * TL_X, j0 = (tile / ntx) * WS_TY;
+  const int nci = m.ni - 1, ncj = m.nj - 1, nck = m.nk - 1;
+  const int actx = min(TL_X, nci - i0), acty = min(WS_TY, ncj - j0);  // cells of this tile
+  const int kb = chunk * kc, ke = min(kb + kc, nck);
+  const int kstart = kb > 0 ? kb - 1 : 0;  // one warm-up layer below the chunk builds the carry
+  const int nlay = ke - kstart;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < WS_NPL; b++) {
+      mbar_init(&pfull[b], WS_NH);
+      mbar_init(&pempty[b], WS_NC);
+    }
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&xfull[b], WS_NC);
+      mbar_init(&xempty[b], WS_NH);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // per patch node: bit0 exists and is summed here, bit1 seam (bit2: on a j line, else on an i line), bits 8..13 pi,
+  // bits 14..17 pj
+  for (int q = tid; q < WS_NRND * WS_NH; q += WS_NC + WS_NH) {
+    int f = 0;
+    if (q < WS_NNODE) {
+      const int pi = q % TL_PX, pj = q / TL_PX;
+      const int i = i0 + pi, j = j0 + pj;
+      f = (pi << 8) | (pj << 14);
+      // a node whose tile cells are all clipped away belongs to the neighbouring tile
+      const bool mine = (pi - 1 < actx && pj - 1 < acty) && i < m.ni && j < m.nj;
+      if (mine) {
+        const bool sj = (j % WS_TY == 0) && j > 0 && j < m.nj - 1, si = (i % TL_X == 0) && i > 0 && i < m.ni - 1;
+        f |= sj ? 7 : (si ? 3 : 1);
+      }
+    }
+    ninfo[q] = f;
+  }
+  for (int q = tid; q < 2 * WS_EX + 3 * WS_NNODE; q += WS_NC + WS_NH) ex[q] = 0.0;  // both exchange buffers and the carry
+  __syncthreads();
+  const long long plane_nodes = (long long)m.ni * m.nj;
+
+  if (tid >= WS_NC) {
+    // ------------------------------------------------------------------------------ helper warpgroup
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_H));
+    const int h = tid - WS_NC;
+#pragma unroll 1
+    for (int p = 0; p < WS_NPL - 1; p++) ws_stage_plane(planes + p * WS_PLANE, &pfull[p], m, x, w, stride, i0, j0, kstart + p, h);
+#pragma unroll 1
+    for (int rel = 0; rel < nlay; rel++) {
+      const int k = kstart + rel;
+      const bool warm = k < kb;
+      {  // plane rel+3 goes where plane rel-1 was
+        const int pr = rel + WS_NPL - 1, u = pr / WS_NPL;
+        if (u >= 1) mbar_wait(&pempty[pr % WS_NPL], (unsigned)((u - 1) & 1));
+        ws_stage_plane(planes + (pr % WS_NPL) * WS_PLANE, &pfull[pr % WS_NPL], m, x, w, stride, i0, j0, kstart + pr, h);
+      }
+      const long long nbase = m.node_off + i0 + (long long)m.ni * j0 + plane_nodes * k;
+      // fixed flags of this thread's nodes of plane k, in flight during the wait (gradient_functors.hpp:223-243)
+      unsigned fxbits = 0;
+      if (!warm) {
+#pragma unroll
+        for (int r = 0; r < WS_NRND; r++) {
+          const int f = ninfo[h + WS_NH * r];
+          if ((f & 3) == 1) fxbits |= (fixed[nbase + (long long)m.ni * ((f >> 14) & 15) + ((f >> 8) & 63)] ? 1u : 0u) << r;
+        }
+      }
+      mbar_wait(&xfull[rel & 1], (unsigned)((rel >> 1) & 1));  // the cells of layer k
+      const double* const exb = ex + (rel & 1) * WS_EX;
+      // node phase: plane k is completed by the bottom contributions of layer k, the top ones start plane k+1
+#pragma unroll 1
+      for (int r = 0; r < WS_NRND; r++) {
+        const int q = h + WS_NH * r;
+        const int f = ninfo[q];
+        if (!(f & 1)) continue;
+        const int pi = (f >> 8) & 63, pj = (f >> 14) & 15;
+        // contribution (local node a, comp c) of cell (dj, di) around this node at exn[(a * 3 + c) * WS_EXPL + dj * WS_EXP + di]
+        const double* const exn = exb + pj * WS_EXP + pi;
+        if (f & 2) {
+          if (warm) continue;
+          // seam node: individual contributions, slot = dk*4 + dj*2 + di around the node
+          double* base;
+          long long pstride, pos0;
+          if (f & 4) {
+            pstride = (long long)m.nk * m.ni;
+            base = seam.J + (long long)((j0 + pj) / WS_TY - 1) * 24 * pstride;
+            pos0 = (long long)k * m.ni + (i0 + pi);
+          } else {
+            pstride = (long long)m.nk * m.nj;
+            base = seam.I + (long long)((i0 + pi) / TL_X - 1) * 24 * pstride;
+            pos0 = (long long)k * m.nj + (j0 + pj);
+          }
+          const long long pos1 = pos0 + ((f & 4) ? m.ni : m.nj);  // the same node of plane k+1
+#pragma unroll
+          for (int c4 = 0; c4 < 4; c4++) {
+            const int di = c4 & 1, dj = c4 >> 1;
+            if (pi - 1 + di < 0 || pi - 1 + di >= actx || pj - 1 + dj < 0 || pj - 1 + dj >= acty) continue;  // not a cell of this tile
+            const int a = (1 - di) + 2 * (1 - dj);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              base[((4 + c4) * 3 + c) * pstride + pos0] = exn[(a * 3 + c) * WS_EXPL + dj * WS_EXP + di];      // dk = 1 cell of plane k
+              base[(c4 * 3 + c) * pstride + pos1] = exn[((a + 4) * 3 + c) * WS_EXPL + dj * WS_EXP + di];      // dk = 0 cell of plane k+1
+            }
+          }
+          continue;
+        }
+        const long long n = nbase + (long long)m.ni * pj + pi;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          double acc = carry[c * WS_NNODE + q], top = 0.0;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; c4++) {
+            const int di = c4 & 1, dj = c4 >> 1;
+            const int a = (1 - di) + 2 * (1 - dj);  // this node's local index in that cell (bottom face)
+            acc += exn[(a * 3 + c) * WS_EXPL + dj * WS_EXP + di];
+            top += exn[((a + 4) * 3 + c) * WS_EXPL + dj * WS_EXP + di];
+          }
+          carry[c * WS_NNODE + q] = top;
+          if (!warm) g[c * stride + n] = ((fxbits >> r) & 1u) ? 0.0 : acc;
+        }
+      }
+      mbar_arrive(&xempty[rel & 1]);
+    }
+    if (ke == nck) {  // top plane of the block: only the cells below it exist
+      const long long nbase = m.node_off + i0 + (long long)m.ni * j0 + plane_nodes * nck;
+#pragma unroll 1
+      for (int r = 0; r < WS_NRND; r++) {
+        const int f = ninfo[h + WS_NH * r];
+        if ((f & 3) != 1) continue;
+        const long long n = nbase + (long long)m.ni * ((f >> 14) & 15) + ((f >> 8) & 63);
+        const bool fx = fixed[n] != 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) g[c * stride + n] = fx ? 0.0 : carry[c * WS_NNODE + h + WS_NH * r];
+      }
+    }
+    // no bulk copy may be in flight when the CTA exits: the last WS_NPL-2 staged planes were never consumed
+    for (int pr = nlay + 1; pr < nlay + WS_NPL - 1; pr++) mbar_wait(&pfull[pr % WS_NPL], (unsigned)((pr / WS_NPL) & 1));
+    return;
+  }
+
+  // ---------------------------------------------------------------------------------- compute warps
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REG_C));
+  const int tx = tid & 31, ty = tid >> 5;
+  const bool active = tx < actx && ty < acty;
+  double val[1] = {0.0};
+  unsigned long long inv = 0;
+  const int par0 = (int)((m.node_off + i0) & 1LL), pni = m.ni & 1, pnj = m.nj & 1;
+  mbar_wait(&pfull[0], 0);
+#pragma unroll 1
+  for (int rel = 0; rel < nlay; rel++) {
+    const int k = kstart + rel;
+    mbar_wait(&pfull[(rel + 1) % WS_NPL], (unsigned)(((rel + 1) / WS_NPL) & 1));
+    if (rel >= 2) mbar_wait(&xempty[rel & 1], (unsigned)(((rel >> 1) - 1) & 1));
+    if (active) {
+      const double* const p0 = planes + (rel % WS_NPL) * WS_PLANE;
+      const double* const p1 = planes + ((rel + 1) % WS_NPL) * WS_PLANE;
+      WsVerts VC, VO;
+      VC.pl[0] = p0;
+      VC.pl[1] = p1;
+      VO.pl[0] = p0 + 3 * WS_PY * TL_ROWP;
+      VO.pl[1] = p1 + 3 * WS_PY * TL_ROWP;
+#pragma unroll
+      for (int dk = 0; dk < 2; dk++)
+#pragma unroll
+        for (int dj = 0; dj < 2; dj++) {
+          // parity of the row's first node: the row is staged from the even node index at or below it
+          const int par = (par0 + pni * ((j0 + ty + dj + pnj * (k + dk)) & 1)) & 1;
+          const int o = (ty + dj) * TL_ROWP + tx + par;
+          VC.o[dk][dj] = o;
+          VO.o[dk][dj] = o;
+        }
+      bool valid;
+      double mm, grad[8][3];
+      if (STRICT) {
+        double vc[8][3], vo[8][3];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            vc[a][r] = VC(a, r);
+            vo[a][r] = VO(a, r);
+          }
+        mm = element_grad_metric<FL_SGRID, STAGE, true>(vc, vo, valid, grad);
+      } else {
+        mm = hex_metric_fast_v<STAGE, true>(VC, VO, valid, grad);
+      }
+      const bool use = valid || STAGE == 0;  // gradient_functors.hpp:391
+      double* const exc = ex + (rel & 1) * WS_EX + (ty + 1) * WS_EXP + (tx + 1);
+#pragma unroll
+      for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) exc[(a * 3 + r) * WS_EXPL] = use ? grad[a][r] : 0.0;
+      if (k >= kb) {
+        val[0] += mm;
+        inv += valid ? 0 : 1;
+        if (em || ef) {
+          const long long e = m.elem_off + (i0 + tx) + (long long)nci * ((j0 + ty) + (long long)ncj * k);
+          if (em) em[e] = mm;
+          if (ef) ef[e] = valid ? 0 : 1;
+        }
+      }
+    }
+    mbar_arrive(&xfull[rel & 1]);
+    mbar_arrive(&pempty[rel % WS_NPL]);
+  }
+  grid_reduce<OpSum, 1, true, 1, WS_NC>(val, inv, R, slot);
+}
+
 // seam nodes: the 8 adjacent cells' contributions in (dk,dj,di) order, as k_grad_gather_sgrid adds them
+template <int TJ>
 __global__ void __launch_bounds__(NT) k_sgrid_seam_sum(const MeshDev m, const SeamDev seam, const uint8_t* __restrict__ fixed,
                                                        double* __restrict__ g, const long long stride, const long long nJ,
                                                        const long long nI) {
@@ -287,7 +683,7 @@ __global__ void __launch_bounds__(NT) k_sgrid_seam_sum(const MeshDev m, const Se
     const long long u = t / m.ni;
     k = (int)(u % m.nk);
     const int line = (int)(u / m.nk);
-    j = (line + 1) * TL_TY;
+    j = (line + 1) * TJ;
     pstride = (long long)m.nk * m.ni;
     base = seam.J + (long long)line * 24 * pstride;
     pos = (long long)k * m.ni + i;
@@ -298,7 +694,7 @@ __global__ void __launch_bounds__(NT) k_sgrid_seam_sum(const MeshDev m, const Se
     k = (int)(u % m.nk);
     const int line = (int)(u / m.nk);
     i = (line + 1) * TL_X;
-    if ((j % TL_TY == 0) && j > 0 && j < m.nj - 1) return;  // crossing: summed with the j line
+    if ((j % TJ == 0) && j > 0 && j < m.nj - 1) return;  // crossing: summed with the j line
     pstride = (long long)m.nk * m.nj;
     base = seam.I + (long long)line * 24 * pstride;
     pos = (long long)k * m.nj + j;
@@ -351,7 +747,7 @@ static int tl_pick_chunk(long long ntiles, int nck) {
   return best_kc;
 }
 
-static size_t tl_seam_doubles_J(const MeshDev& m) { return (size_t)tl_lines(m.nj, TL_TY) * 24 * m.nk * m.ni; }
+static size_t tl_seam_doubles_J(const MeshDev& m) { return (size_t)tl_lines(m.nj, WS_TY) * 24 * m.nk * m.ni; }
 static size_t tl_seam_doubles_I(const MeshDev& m) { return (size_t)tl_lines(m.ni, TL_X) * 24 * m.nk * m.nj; }
 
 // bytes of seam scratch the fused structured gradient needs for this block
@@ -363,30 +759,30 @@ static bool launch_grad_fused_sgrid(cudaStream_t st, const MeshDev& m, int stage
                                     long long stride, const uint8_t* fixed, double* g, const Reduce& R, int slot,
                                     double* scratch, double* em, int32_t* ef) {
   if (m.kind != KIND_SGRID || m.ni < 2 || m.nj < 2 || m.nk < 2 || !scratch) return false;
-  if (((uintptr_t)x & 15) || ((uintptr_t)w & 15) || (stride & 1)) return false;  // 16-byte staging needs even plane starts
+  // 16-byte bulk copies need even plane starts
+  if (((uintptr_t)x & 15) || ((uintptr_t)w & 15) || (stride & 1)) return false;
   const int nci = m.ni - 1, ncj = m.nj - 1, nck = m.nk - 1;
-  const int ntx = (nci + TL_X - 1) / TL_X, nty = (ncj + TL_TY - 1) / TL_TY;
+  const int ntx = (nci + TL_X - 1) / TL_X, nty = (ncj + WS_TY - 1) / WS_TY;
   const long long ntiles = (long long)ntx * nty;
   const int kc = tl_pick_chunk(ntiles, nck);
   const int nchunks = (nck + kc - 1) / kc;
   const long long grid = ntiles * nchunks;
   if (grid > R.max_blocks || grid > 0x7fffffffLL) return false;
-  constexpr size_t smem = (size_t)(3 * 6 * TL_PY * TL_ROWP + 24 * TL_NCELL + 3 * TL_NNODE) * sizeof(double) + TL_NNODE * sizeof(int);
   SeamDev sd;
   sd.J = scratch;
   sd.I = scratch + tl_seam_doubles_J(m);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_sgrid_tile_grad<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_sgrid_tile_grad<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_sgrid_tile_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
+    cudaFuncSetAttribute(k_sgrid_tile_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
     attr_set = true;
   }
-  const dim3 block(TL_X, TL_Y, 1);
   if (stage == 0)
-    k_sgrid_tile_grad<0><<<(unsigned)grid, block, smem, st>>>(m, x, w, stride, fixed, g, sd, ntx, nty, kc, R, slot, em, ef);
+    k_sgrid_tile_ws<0><<<(unsigned)grid, WS_NC + WS_NH, WS_SMEM, st>>>(m, x, w, stride, fixed, g, sd, ntx, nty, kc, R, slot, em, ef);
   else
-    k_sgrid_tile_grad<1><<<(unsigned)grid, block, smem, st>>>(m, x, w, stride, fixed, g, sd, ntx, nty, kc, R, slot, em, ef);
-  const long long nJ = (long long)tl_lines(m.nj, TL_TY) * m.nk * m.ni, nI = (long long)tl_lines(m.ni, TL_X) * m.nk * m.nj;
-  if (nJ + nI > 0) k_sgrid_seam_sum<<<(unsigned)((nJ + nI + NT - 1) / NT), NT, 0, st>>>(m, sd, fixed, g, stride, nJ, nI);
+    k_sgrid_tile_ws<1><<<(unsigned)grid, WS_NC + WS_NH, WS_SMEM, st>>>(m, x, w, stride, fixed, g, sd, ntx, nty, kc, R, slot, em, ef);
+  const long long nJ = (long long)tl_lines(m.nj, WS_TY) * m.nk * m.ni, nI = (long long)tl_lines(m.ni, TL_X) * m.nk * m.nj;
+  if (nJ + nI > 0)
+    k_sgrid_seam_sum<WS_TY><<<(unsigned)((nJ + nI + NT - 1) / NT), NT, 0, st>>>(m, sd, fixed, g, stride, nJ, nI);
   return true;
 }

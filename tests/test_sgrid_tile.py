@@ -74,7 +74,7 @@ def test_fused_equals_two_pass_and_oracle(nn, stage, strict):
 def test_fused_at_128_cubed_matches_oracle():
     """BASELINE config 2 size (128^3 cells): 4 x 8 tiles, several k chunks, 32-bit/64-bit index paths."""
     nn = (129, 129, 129)
-    X, W = block_coords(nn, 0.5, seed=11)
+    X, W = block_coords(nn, 0.3, seed=11)
     f = build(pb.api, nn, X, W, True, {"cache_metric": 0})
     o = build(oracle, nn, X, W, True, {"real_is_double": 1})
     mf, nf = f.metric_and_gradient(1)
@@ -82,7 +82,8 @@ def test_fused_at_128_cubed_matches_oracle():
     assert nf == no
     assert abs(mf - mo) <= 1e-12 * abs(mo)
     gf, go = f.download("cg_g"), o.download("cg_g")
-    assert np.max(np.abs(gf - go)) <= 1e-12 * np.max(np.abs(go))
+    err = np.max(np.abs(gf - go)) / np.max(np.abs(go))
+    assert err <= 1e-12, err
     s = build(pb.api, nn, X, W, True, {"cache_metric": 0, "strict_fp": 1})
     s.metric_and_gradient(1)
     assert np.array_equal(s.download("cg_g"), go)
