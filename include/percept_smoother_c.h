@@ -119,8 +119,13 @@ int pms_get_node_elem_csr(const pms_ctx* ctx, int64_t* row_ptr, int64_t* entries
 /* block = -1 addresses the whole (unstructured or single-block) mesh.          */
 int pms_field_upload(pms_ctx* ctx, const char* name, int block, const double* host, int layout);
 int pms_field_download(pms_ctx* ctx, const char* name, int block, double* host, int layout);
-/* Device view of a field: component c of local node n is dptr[c*comp_stride+n]. */
+/* Device view of a field: component c of local node n is dptr[c*comp_stride+n].  The caller may read and write
+ * through the pointer between calls (on the ctx stream, or after pms_synchronize).  From this call on the library
+ * assumes the field may have changed before EVERY later call: cached metrics, the precomputed gradient and the
+ * search-direction scalars that depend on it are not re-used across calls (results stay correct, per-call caching of
+ * that field is lost) until pms_field_release_ptr(name) ends the aliasing.                                        */
 int pms_field_device_ptr(pms_ctx* ctx, const char* name, double** dptr, size_t* comp_stride);
+int pms_field_release_ptr(pms_ctx* ctx, const char* name);
 /* Asynchronous SoA transfers (pinned host memory) for callers that evaluate many coordinate sets: the read-back of one
  * evaluation and the upload of a later one run beside the kernels (PCIe is full duplex; three streams).  Both go through
  * device staging buffers, so kernels queued afterwards never race with a copy in flight.

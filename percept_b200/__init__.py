@@ -22,10 +22,19 @@ def _load():
     return _C.CDLL(LIB_PATH)
 
 
-lib = _load()
-api = Api(lib, "pms_", product=True)
+# `lib` (the ctypes handle of libpms.so) and `api` (its bound entry points) are created on first use, so that
+# importing a submodule that needs no device code (percept_b200.capi, .partition, .exodus) does not map the CUDA
+# library into the process — bench.py's CPU reference arm relies on that.
+def __getattr__(name):
+    if name in ("lib", "api"):
+        g = globals()
+        if "lib" not in g:
+            g["lib"] = _load()
+            g["api"] = Api(g["lib"], "pms_", product=True)
+        return g[name]
+    raise AttributeError(f"module 'percept_b200' has no attribute {name!r}")
 
 
 def create(device=0):
     """New smoother context on CUDA device `device`."""
-    return api.create(device)
+    return __getattr__("api").create(device)

@@ -95,6 +95,7 @@ class Api:
         "transfer_wait": [],
         "total_metric_multi": [C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_size_t)],
         "field_device_ptr": [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
+        "field_release_ptr": [C.c_char_p],
         "comm_init": [C.c_void_p, C.c_int, C.c_int],
         "set_halo": [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         "halo_exchange": [C.c_char_p],
@@ -398,6 +399,9 @@ class Ctx:
         p, s = C.c_void_p(), C.c_size_t()
         self._call("field_device_ptr", name.encode(), C.byref(p), C.byref(s))
         return p.value, s.value
+
+    def field_release_ptr(self, name):
+        self._call("field_release_ptr", name.encode())
 
     def launch_count(self):
         n = C.c_uint64()

@@ -1180,11 +1180,20 @@ struct Driver {
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
-// every entry point runs on the context's own device (a process may hold contexts on several GPUs)
+// Every entry point runs on the context's own device (a process may hold contexts on several GPUs).  A field whose raw
+// device pointer has been handed out (pms_field_device_ptr) may have been written behind the library's back since the
+// last call: its version is bumped on every entry, so the metric cache, the precomputed gradient and the search-
+// direction scalars keyed on it are never re-used across calls (until pms_field_release_ptr).
+static inline void pms_enter(pms_ctx* c) {
+  if (c->stream) cudaSetDevice(c->device);
+  if (c->n_aliased)
+    for (auto& kv : c->fields)
+      if (kv.second.aliased) kv.second.version++;
+}
 #define PMS_TRY \
   if (!c) return PMS_ERR_ARG; \
   try {      \
-    if (c->stream) cudaSetDevice(c->device);
+    pms_enter(c);
 #define PMS_CATCH                   \
   }                                 \
   catch (const PmsError& e) {       \
@@ -1826,7 +1835,23 @@ int pms_field_device_ptr(pms_ctx* c, const char* name, double** dptr, size_t* co
   DField& f = c->field(name);
   *dptr = f.d;
   *comp_stride = (size_t)c->Npad;
-  f.version++;  // the caller may write through the pointer
+  f.version++;  // the caller may write through the pointer ...
+  if (!f.aliased) {  // ... now and later: see pms_enter
+    f.aliased = true;
+    c->n_aliased++;
+  }
+  PMS_CATCH
+}
+
+int pms_field_release_ptr(pms_ctx* c, const char* name) {
+  PMS_TRY
+  require_committed(c);
+  DField& f = c->field(name);
+  if (f.aliased) {
+    f.aliased = false;
+    c->n_aliased--;
+  }
+  f.version++;
   PMS_CATCH
 }
 

@@ -44,6 +44,7 @@ struct DField {
   int ncomp = 0;
   double* d = nullptr;
   uint64_t version = 0;  // bumped on every write; keys the metric cache
+  bool aliased = false;  // raw device pointer handed out: bumped on every API entry as well
 };
 
 enum Family { FAM_METRIC = 0, FAM_GRADIENT, FAM_BLAS1, FAM_UPDATE, FAM_ALPHA0, FAM_EDGE, FAM_HALO, FAM_REFINE, FAM_COUNT };
@@ -96,6 +97,7 @@ struct pms_ctx {
   long long n_surf_nodes = 0;
 
   std::map<std::string, DField> fields;
+  int n_aliased = 0;
 
   // reductions
   pmsk::Reduce R{};

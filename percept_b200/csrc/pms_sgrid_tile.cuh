@@ -1,49 +1,40 @@
-// pms_sgrid_tile.cuh — structured-block tile kernels (included by pms_kernels.cu inside namespace PMS_NS).
+// pms_sgrid_tile.cuh — structured-block tile kernel (included by pms_kernels.cu inside namespace PMS_NS).
 //
 // One-pass fused metric + nodal gradient of a StructuredGrid block: replaces the element pass + 192 B/cell scratch +
 // node gather of the two-pass scheme (reference functor: gradient_functors.hpp:349-407, whose 24 Kokkos::atomic_add per
 // cell become an in-CTA gather in a FIXED order).
 //
-//  * A CTA of 32 x 8 threads owns a tile of 32 x (8*TL_NSUB) cells and marches a chunk of k-layers.  The node planes
-//    k and k+1 of x and of the reference mesh w (the tile's cells + a one-node halo: 33 x (8*TL_NSUB+1) nodes, 6
-//    component planes) live in shared memory; plane k+2 is in flight while layer k is evaluated: 128-bit cp.async
-//    (LDGSTS.128) over the 16-byte-aligned span of every node row, three rotating plane buffers.  Each node is fetched
-//    once per CTA instead of 8 times, and there is no per-vertex address arithmetic.
-//  * Each thread evaluates TL_NSUB cells per layer (vertices read in place from the staged planes) and writes the cell's
-//    24 contributions to a shared-memory exchange array ex[a*3+r][cell].
+//  * A CTA owns a tile of 32 x 8 cells and marches a chunk of k-layers.  The node planes of x and of the reference mesh
+//    w (the tile's cells + a one-node halo: 33 x 9 nodes, 6 component planes) are staged in shared memory by TMA bulk
+//    copies (cp.async.bulk -> SASS UBLKCP, one copy per node row: the 16-byte-aligned 288-byte span around its 33
+//    nodes), four rotating plane buffers, completion on mbarriers.  Each node is fetched once per CTA instead of 8
+//    times, and there is no per-vertex address arithmetic.
+//  * Warp specialisation: 8 compute warps (setmaxnreg 232) evaluate one cell per thread per layer, vertices read in place
+//    from the staged planes, and write the cell's 24 contributions to one of TWO exchange buffers in shared memory; they
+//    execute no CTA barrier.  4 helper warps (setmaxnreg 40) issue the bulk copies two-three planes ahead and run the
+//    node phase of layer k while the compute warps are already in layer k+1.  (A first version alternated a cell phase
+//    and a node phase between __syncthreads: ncu showed the FP64 pipe idle 30 % of the time — node phase 13 %, warps
+//    waiting at the barrier for the slower warp of their scheduler pair 17 % — and it was no faster than the two-pass
+//    path; profiles/r02_sgrid_tile.md.)
 //  * Node phase: every node of the tile's patch sums the contributions of its adjacent cells in the fixed (dk,dj,di)
 //    order of k_grad_gather_sgrid (= ascending cell id = the serial reference loop): the four cells of layer k-1 were
 //    summed one layer earlier into a carry held in shared memory, the four cells of layer k are added to it and the node
 //    of plane k is final -> one coalesced store per component, fixed nodes zeroed (gradient_functors.hpp:223-243).
 //    The sequence of floating-point additions per node is exactly that of the two-pass path, so the result is bitwise
 //    identical to it (and, in the strict build, to the CPU oracle).
-//  * Nodes on a line between two tiles ("seam" nodes: 1/32 + 1/(8*TL_NSUB) of all nodes) receive contributions from two
-//    or four CTAs.  Adding per-tile partial sums would change the order of additions, so each CTA stores the
-//    individual contributions of its own cells into a compact seam scratch (slot = the cell's position (dk,dj,di)
-//    around the node) and k_sgrid_seam_sum adds the 8 slots in order.  No atomics, no index tables; the scratch is
-//    (1/32 + 1/(8*TL_NSUB)) * 192 B per node instead of 192 B per cell.
+//  * Nodes on a line between two tiles ("seam" nodes: 1/32 + 1/8 of all nodes) receive contributions from two or four
+//    CTAs.  Adding per-tile partial sums would change the order of additions, so each CTA stores the individual
+//    contributions of its own cells into a compact seam scratch (slot = the cell's position (dk,dj,di) around the
+//    node) and k_sgrid_seam_sum adds the 8 slots in order.  No atomics, no index tables; the scratch is
+//    (1/32 + 1/8) * 192 B per node instead of 192 B per cell.
 //  * k is cut into chunks so that tiles x chunks fill the SMs evenly; a chunk that does not start at k = 0 first
 //    re-evaluates the layer below it to build the carry (nothing of that layer is stored or counted).
-//
-// The same staging serves the metric-only kernels of the line search (k_sgrid_tile_metric).
 #pragma once
 
-#ifndef TL_YDIM
-#define TL_YDIM 8
-#endif
-#ifndef TL_NSUB
-#define TL_NSUB 2
-#endif
-#ifndef TL_MINB
-#define TL_MINB 1
-#endif
-constexpr int TL_X = 32, TL_Y = TL_YDIM;  // threads of a CTA = cells of one sub-row step
-constexpr int TL_TY = TL_Y * TL_NSUB;            // cells per tile in j
-constexpr int TL_PX = TL_X + 1, TL_PY = TL_TY + 1;  // node patch of a tile
-constexpr int TL_ROWP = 36;                      // staged row: 18 x 16 B covering 33 nodes from an even node index
-constexpr int TL_NTH = TL_X * TL_Y;
-constexpr int TL_NCELL = TL_X * TL_TY;
-constexpr int TL_NNODE = TL_PX * TL_PY;
+constexpr int TL_X = 32;               // cells of a tile in i = lanes of a warp
+constexpr int TL_PX = TL_X + 1;        // nodes of its patch in i
+constexpr int TL_ROWP = 36;            // staged row: 18 x 16 B covering 33 nodes from an even node index
+
 
 __host__ __device__ inline int tl_lines(int n, int t) { return n >= 3 ? (n - 2) / t : 0; }  // interior tile lines among n nodes
 
@@ -80,321 +71,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 }
 
 // one staged node plane: NARR*3 component planes of TL_PY rows of TL_ROWP doubles, then TL_PY rows of 64 mask bytes
-template <int NARR>
-struct TilePlane {
-  static constexpr int ROWS_D = NARR * 3 * TL_PY;
-  static constexpr int DOUBLES = ROWS_D * TL_ROWP + TL_PY * 8;
-};
 
-// Warp 0 stages node plane kp of the tile at (i0, j0): every node row is ONE bulk copy of the 16-byte-aligned span that
-// covers its 33 nodes (36 doubles from the even node index at or below the row's first node; 64 mask bytes from the
-// 16-byte boundary below it).  Every lane arms the plane's mbarrier with the bytes of its own rows (32 arrivals).
-template <int NARR>
-__device__ __forceinline__ void tl_stage_plane(double* buf, unsigned long long* bar, const MeshDev& m, const double* a0,
-                                               const double* a1, const double* a2, const uint8_t* fixed, const long long stride,
-                                               const int i0, const int j0, const int kp, const int lane) {
-  constexpr int NL = (TilePlane<NARR>::ROWS_D + TL_PY + 31) / 32;
-  const void* src[NL];
-  unsigned dst[NL], nb[NL], total = 0;
-  const int rows = min(TL_PY, m.nj - j0);
-#pragma unroll
-  for (int it = 0; it < NL; it++) {
-    const int line = lane + 32 * it;
-    const int ac = line / TL_PY, row = line % TL_PY;  // ac = array * 3 + component; ac == NARR*3: the fixed mask
-    nb[it] = 0;
-    src[it] = nullptr;
-    dst[it] = 0;
-    if (kp < m.nk && ac <= NARR * 3 && row < rows) {
-      const long long nrow = m.node_off + i0 + (long long)m.ni * ((j0 + row) + (long long)m.nj * kp);
-      if (ac < NARR * 3) {
-        const long long a = nrow & ~1LL;
-        const long long n = stride - a < TL_ROWP ? stride - a : TL_ROWP;
-        const double* base = ac < 3 ? a0 : (ac < 6 ? a1 : a2);
-        src[it] = base + (ac % 3) * stride + a;
-        dst[it] = smem_u32(buf + (ac * TL_PY + row) * TL_ROWP);
-        nb[it] = (unsigned)n * 8u;
-      } else {
-        const long long a = nrow & ~15LL;
-        const long long n = stride - a < 64 ? stride - a : 64;
-        src[it] = fixed + a;
-        dst[it] = smem_u32(buf + TilePlane<NARR>::ROWS_D * TL_ROWP + row * 8);
-        nb[it] = (unsigned)n;
-      }
-      total += nb[it];
-    }
-  }
-  mbar_arrive_expect_tx(bar, total);
-#pragma unroll
-  for (int it = 0; it < NL; it++)
-    if (nb[it])
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst[it]),
-                   "l"(src[it]), "r"(nb[it]), "r"(smem_u32(bar))
-                   : "memory");
-}
-
-// vertices of one cell read in place from two staged planes: V(p, r), p = di + 2 dj + 4 dk
-struct TileVerts {
-  const double* pl[2];  // plane k / k+1, already offset to this array's component 0
-  int o[2][2];          // [dk][dj]: row * TL_ROWP + column of the cell's (di = 0) node
-  PMS_DI double operator()(int p, int r) const { return pl[p >> 2][r * (TL_PY * TL_ROWP) + o[p >> 2][(p >> 1) & 1] + (p & 1)]; }
-};
-
-// node slots of a thread: round r < TL_NSUB -> patch node (tx, ty + 8 r); round TL_NSUB -> row TL_TY (ty == 0) and the
-// column pi = TL_X (ty == 1, pj = tx)
-__device__ __forceinline__ bool tl_slot_node(const int r, const int tx, const int ty, int& pi, int& pj) {
-  if (r < TL_NSUB) {
-    pi = tx;
-    pj = ty + TL_Y * r;
-    return true;
-  }
-  if (ty == 0) {
-    pi = tx;
-    pj = TL_TY;
-    return true;
-  }
-  pi = TL_X;
-  pj = tx;
-  return ty == 1 && tx < TL_PY;
-}
-
-template <int STAGE>
-__global__ void __launch_bounds__(TL_NTH, TL_MINB) k_sgrid_tile_grad(const MeshDev m, const double* __restrict__ x,
-                                                               const double* __restrict__ w, const long long stride,
-                                                               const uint8_t* __restrict__ fixed, double* __restrict__ g,
-                                                               const SeamDev seam, const int ntx, const int nty, const int kc,
-                                                               const Reduce R, const int slot, double* __restrict__ em,
-                                                               int32_t* __restrict__ ef) {
-  extern __shared__ double sm[];
-  constexpr int PLANE = TilePlane<2>::DOUBLES;
-  constexpr int NSLOT = (TL_NSUB + 1) * TL_NTH;
-  double* const planes = sm;                 // [3][PLANE]
-  double* const ex = sm + 3 * PLANE;         // [24][TL_NCELL]
-  double* const carry = ex + 24 * TL_NCELL;  // [3][NSLOT]
-  int* const info = reinterpret_cast<int*>(carry + 3 * NSLOT);                             // [NSLOT]
-  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(info + NSLOT);    // [3]
-  double* const cellm = reinterpret_cast<double*>(bars + 4);                               // [TL_NCELL] metric of the layer's cells
-  int* const rowctr = reinterpret_cast<int*>(cellm + TL_NCELL);                            // [2] next cell row to evaluate
-  uint8_t* const cellv = reinterpret_cast<uint8_t*>(rowctr + 2);                           // [TL_NCELL] 1 = valid
-  const int tx = threadIdx.x, ty = threadIdx.y, tid = tx + TL_X * ty;
-  const int tile = blockIdx.x % (ntx * nty), chunk = blockIdx.x / (ntx * nty);
-  const int i0 = (tile % ntx) * TL_X, j0 = (tile / ntx) * TL_TY;
-  const int nci = m.ni - 1, ncj = m.nj - 1, nck = m.nk - 1;
-  const int actx = min(TL_X, nci - i0), acty = min(TL_TY, ncj - j0);  // cells of this tile
-  const int kb = chunk * kc, ke = min(kb + kc, nck);
-  const int kstart = kb > 0 ? kb - 1 : 0;  // one warm-up layer below the chunk builds the carry
-
-  if (tid == 0) {
-    rowctr[0] = rowctr[1] = 0;
-#pragma unroll
-    for (int b = 0; b < 3; b++) mbar_init(&bars[b], 32);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // per node slot: bit0 exists, bit1 seam (bit2: on a j line, else on an i line), bits 4..7 adjacent tile cells (dj*2+di)
-#pragma unroll
-  for (int r = 0; r <= TL_NSUB; r++) {
-    int pi, pj, f = 0;
-    if (tl_slot_node(r, tx, ty, pi, pj)) {
-      const int i = i0 + pi, j = j0 + pj;
-      if (i < m.ni && j < m.nj) {
-        f = 1;
-        const bool sj = (j % TL_TY == 0) && j > 0 && j < m.nj - 1, si = (i % TL_X == 0) && i > 0 && i < m.ni - 1;
-        if (sj)
-          f |= 2 | 4;
-        else if (si)
-          f |= 2;
-#pragma unroll
-        for (int c4 = 0; c4 < 4; c4++) {
-          const int cx = pi - 1 + (c4 & 1), cy = pj - 1 + (c4 >> 1);
-          if (cx >= 0 && cx < actx && cy >= 0 && cy < acty) f |= 16 << c4;
-        }
-      }
-    }
-    const int q = r * TL_NTH + tid;
-    info[q] = f;
-    carry[q] = 0.0;
-    carry[NSLOT + q] = 0.0;
-    carry[2 * NSLOT + q] = 0.0;
-  }
-  __syncthreads();
-  if (ty == 0) {
-    tl_stage_plane<2>(planes + (kstart % 3) * PLANE, &bars[kstart % 3], m, x, w, nullptr, fixed, stride, i0, j0, kstart, tx);
-    tl_stage_plane<2>(planes + ((kstart + 1) % 3) * PLANE, &bars[(kstart + 1) % 3], m, x, w, nullptr, fixed, stride, i0, j0,
-                      kstart + 1, tx);
-  }
-  mbar_wait(&bars[kstart % 3], 0);
-
-  double val[1] = {0.0};
-  unsigned long long inv = 0;
-  const long long plane_nodes = (long long)m.ni * m.nj;
-  const int par0 = (int)((m.node_off + i0) & 1LL), pni = m.ni & 1, pnj = m.nj & 1;
-
-  for (int k = kstart; k < ke; k++) {
-    const bool warm = k < kb;
-    __syncthreads();  // everyone is done with layer k-1: ex, carry and the buffer of plane k-1 are free
-    if (ty == 0)
-      tl_stage_plane<2>(planes + ((k + 2) % 3) * PLANE, &bars[(k + 2) % 3], m, x, w, nullptr, fixed, stride, i0, j0, k + 2, tx);
-    mbar_wait(&bars[(k + 1) % 3], (unsigned)(((k + 1 - kstart) / 3) & 1));
-    const double* const p0 = planes + (k % 3) * PLANE;
-    const double* const p1 = planes + ((k + 1) % 3) * PLANE;
-
-    // Cell rows are handed out dynamically (one row of 32 cells per request): with two warps per scheduler and a
-    // barrier per layer, a static split leaves the faster warp of each pair idle at the barrier for ~17 % of the time.
-    // Values do not depend on which warp evaluates a row; the metric is summed later by a fixed thread per cell.
-    if (tid == 0) rowctr[(k + 1) & 1] = 0;
-#pragma unroll 1
-    for (;;) {
-      int cj = 0;
-      if (tx == 0) cj = atomicAdd(&rowctr[k & 1], 1);
-      cj = __shfl_sync(0xffffffffu, cj, 0);
-      if (cj >= acty) break;
-      if (tx >= actx) continue;
-      TileVerts VC, VO;
-      VC.pl[0] = p0;
-      VC.pl[1] = p1;
-      VO.pl[0] = p0 + 3 * TL_PY * TL_ROWP;
-      VO.pl[1] = p1 + 3 * TL_PY * TL_ROWP;
-#pragma unroll
-      for (int dk = 0; dk < 2; dk++)
-#pragma unroll
-        for (int dj = 0; dj < 2; dj++) {
-          // parity of the row's first node: the row is staged from the even node index at or below it
-          const int par = (par0 + pni * ((j0 + cj + dj + pnj * (k + dk)) & 1)) & 1;
-          const int o = (cj + dj) * TL_ROWP + tx + par;
-          VC.o[dk][dj] = o;
-          VO.o[dk][dj] = o;
-        }
-      bool valid;
-      double mm, grad[8][3];
-      if (STRICT) {
-        double vc[8][3], vo[8][3];
-#pragma unroll
-        for (int a = 0; a < 8; a++)
-#pragma unroll
-          for (int r = 0; r < 3; r++) {
-            vc[a][r] = VC(a, r);
-            vo[a][r] = VO(a, r);
-          }
-        mm = element_grad_metric<FL_SGRID, STAGE, true>(vc, vo, valid, grad);
-      } else {
-        mm = hex_metric_fast_v<STAGE, true>(VC, VO, valid, grad);
-      }
-      const bool use = valid || STAGE == 0;  // gradient_functors.hpp:391
-      const int cell = cj * TL_X + tx;
-#pragma unroll
-      for (int a = 0; a < 8; a++)
-#pragma unroll
-        for (int r = 0; r < 3; r++) ex[(a * 3 + r) * TL_NCELL + cell] = use ? grad[a][r] : 0.0;
-      cellm[cell] = mm;
-      cellv[cell] = valid ? 1 : 0;
-      if (!warm && (em || ef)) {
-        const long long e = m.elem_off + (i0 + tx) + (long long)nci * ((j0 + cj) + (long long)ncj * k);
-        if (em) em[e] = mm;
-        if (ef) ef[e] = valid ? 0 : 1;
-      }
-    }
-    __syncthreads();
-
-    // node phase: plane k is completed by the bottom contributions of layer k, the top ones start plane k+1
-    const long long nbase = m.node_off + i0 + (long long)m.ni * j0 + plane_nodes * k;
-    const uint8_t* const fx_rows = reinterpret_cast<const uint8_t*>(p0 + TilePlane<2>::ROWS_D * TL_ROWP);
-#pragma unroll
-    for (int r = 0; r <= TL_NSUB; r++) {
-      const int q = r * TL_NTH + tid;
-      if (r < TL_NSUB && !warm && tx < actx && ty + TL_Y * r < acty) {  // total_element_metric.cpp:271-307
-        val[0] += cellm[(ty + TL_Y * r) * TL_X + tx];
-        inv += cellv[(ty + TL_Y * r) * TL_X + tx] ? 0 : 1;
-      }
-      const int f = info[q];
-      if (!(f & 1)) continue;
-      int pi, pj;
-      tl_slot_node(r, tx, ty, pi, pj);
-      const double* const exn = ex + (pj - 1) * TL_X + (pi - 1);  // cell (dj, di) of this node at + dj * TL_X + di
-      if (f & 2) {
-        if (warm) continue;
-        // seam node: individual contributions, slot = dk*4 + dj*2 + di around the node
-        const int i = i0 + pi, j = j0 + pj;
-        double* base;
-        long long pstride, pos0;
-        if (f & 4) {
-          pstride = (long long)m.nk * m.ni;
-          base = seam.J + (long long)(j / TL_TY - 1) * 24 * pstride;
-          pos0 = (long long)k * m.ni + i;
-        } else {
-          pstride = (long long)m.nk * m.nj;
-          base = seam.I + (long long)(i / TL_X - 1) * 24 * pstride;
-          pos0 = (long long)k * m.nj + j;
-        }
-        const long long pos1 = pos0 + ((f & 4) ? m.ni : m.nj);  // the same node of plane k+1
-#pragma unroll
-        for (int c4 = 0; c4 < 4; c4++) {
-          if (!(f & (16 << c4))) continue;
-          const int di = c4 & 1, dj = c4 >> 1;
-          const int a = (1 - di) + 2 * (1 - dj);
-#pragma unroll
-          for (int rr = 0; rr < 3; rr++) {
-            base[((4 + c4) * 3 + rr) * pstride + pos0] = exn[(a * 3 + rr) * TL_NCELL + dj * TL_X + di];       // dk = 1 cell of plane k
-            base[(c4 * 3 + rr) * pstride + pos1] = exn[((a + 4) * 3 + rr) * TL_NCELL + dj * TL_X + di];       // dk = 0 cell of plane k+1
-          }
-        }
-        continue;
-      }
-      double acc[3], top[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int rr = 0; rr < 3; rr++) acc[rr] = carry[rr * NSLOT + q];
-#pragma unroll
-      for (int c4 = 0; c4 < 4; c4++) {
-        if (!(f & (16 << c4))) continue;
-        const int di = c4 & 1, dj = c4 >> 1;
-        const int a = (1 - di) + 2 * (1 - dj);  // this node's local index in that cell (bottom face)
-#pragma unroll
-        for (int rr = 0; rr < 3; rr++) {
-          acc[rr] += exn[(a * 3 + rr) * TL_NCELL + dj * TL_X + di];
-          top[rr] += exn[((a + 4) * 3 + rr) * TL_NCELL + dj * TL_X + di];
-        }
-      }
-#pragma unroll
-      for (int rr = 0; rr < 3; rr++) carry[rr * NSLOT + q] = top[rr];
-      if (!warm) {
-        const long long n = nbase + (long long)m.ni * pj + pi;
-        const bool fx = fx_rows[pj * 64 + (int)((nbase + (long long)m.ni * pj) & 15LL) + pi] != 0;  // fixup: gradient_functors.hpp:223-243
-#pragma unroll
-        for (int rr = 0; rr < 3; rr++) g[rr * stride + n] = fx ? 0.0 : acc[rr];
-      }
-    }
-    // (the __syncthreads at the top of the next layer orders this phase before ex / carry are written again)
-  }
-  if (ke == nck) {  // top plane of the block: only the cells below it exist
-    __syncthreads();
-    const long long nbase = m.node_off + i0 + (long long)m.ni * j0 + plane_nodes * nck;
-#pragma unroll
-    for (int r = 0; r <= TL_NSUB; r++) {
-      const int q = r * TL_NTH + tid;
-      const int f = info[q];
-      if (!(f & 1) || (f & 2)) continue;
-      int pi, pj;
-      tl_slot_node(r, tx, ty, pi, pj);
-      const long long n = nbase + (long long)m.ni * pj + pi;
-      const bool fx = fixed[n] != 0;
-#pragma unroll
-      for (int rr = 0; rr < 3; rr++) g[rr * stride + n] = fx ? 0.0 : carry[rr * NSLOT + q];
-    }
-  }
-  // the last staged planes (k+1 of the last layer and k+2) must have landed before the CTA may exit
-  mbar_wait(&bars[(ke + 1) % 3], (unsigned)(((ke + 1 - kstart) / 3) & 1));
-  grid_reduce<OpSum, 1, true>(val, inv, R, slot);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Warp-specialised form (the one the launcher uses).  The kernel above alternates, per layer, an FP64-bound cell phase
-// and a latency-bound node phase separated by CTA barriers: ncu showed the FP64 pipe idle for 30 % of the time (node
-// phase 13 %, warps waiting at the barrier for the slower warp of their scheduler pair 17 %).  Here
-//   * 8 compute warps (setmaxnreg 232) evaluate one cell per thread per layer and write its 24 contributions to one of
-//     TWO exchange buffers; they never execute a CTA barrier,
-//   * 4 helper warps (setmaxnreg 40): warp 8 stages the node planes with TMA bulk copies two planes ahead; all four run
-//     the node phase of layer k (ordered gather, carry, stores, seam scratch) while the compute warps are in layer k+1.
-// Hand-off through mbarriers: pfull[3] (TMA complete_tx), pempty[3] (everyone done with a plane buffer),
-// xfull[2] / xempty[2] (exchange buffer written / gathered).  Tile = 32 x 8 cells, one cell per compute thread.
-// ------------------------------------------------------------------------------------------------------------------
 constexpr int WS_TY = 8;                                  // cell rows of a tile
 constexpr int WS_PY = WS_TY + 1;                          // node rows of its patch
 constexpr int WS_NC = 256, WS_NH = 128;                   // compute / helper threads
