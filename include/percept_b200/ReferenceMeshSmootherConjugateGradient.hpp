@@ -27,6 +27,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <typeinfo>
 #include <vector>
 
 #include "../percept_fixtures_c.h"
@@ -448,7 +449,35 @@ class MeshSmootherImpl {  // MeshSmoother.hpp:35-80
     return geometry_fixed_flag(m_meshGeometry, node);
   }
 
+  /// project_delta_to_tangent_plane(node, delta, norm) (MeshSmoother.hpp:74, MeshSmoother.cpp:437-460): remove from
+  /// delta its component along the surface normal at the node; norm (optional) receives the normal.  No geometry: no-op.
+  /// The normal comes from the device evaluator (pms_get_surface_normals, cached until invalidate_normals()).
+  void project_delta_to_tangent_plane(size_t node, double* delta, double* norm = 0) {
+    if (!has_geometry(m_meshGeometry)) return;
+    const size_t N = m_eMesh->num_nodes_local();
+    if (m_normals.size() != 3 * N) {
+      m_normals.assign(3 * N, 0.0);
+      check(m_eMesh->ctx(), pms_get_surface_normals(m_eMesh->ctx(), m_normals.data()));
+    }
+    double dot = 0.0;
+    for (int i = 0; i < m_eMesh->get_spatial_dim(); i++) dot += delta[i] * m_normals[i * N + node];
+    for (int i = 0; i < m_eMesh->get_spatial_dim(); i++) {
+      delta[i] -= dot * m_normals[i * N + node];
+      if (norm) norm[i] = m_normals[i * N + node];
+    }
+  }
+  void invalidate_normals() { m_normals.clear(); }
+  /// snap_to(node, coordinate, reset) (MeshSmoother.hpp:79, MeshSmoother.cpp:517-563): if reset is true the node's
+  /// coordinates are not modified and only the snapped position is returned in coordinate.
+  void snap_to(size_t node, double* coordinate, bool reset = false) const {
+    if (!has_geometry(m_meshGeometry)) return;
+    check(m_eMesh->ctx(), pms_snap_point(m_eMesh->ctx(), node, coordinate, reset ? 1 : 0));
+  }
+
  protected:
+  std::vector<double> m_normals;
+  static bool has_geometry(MeshGeometry* g) { return g != nullptr; }
+  static bool has_geometry(SGridMeshGeometry*) { throw std::runtime_error("not impl"); }  // the reference's StructuredGrid specialisation
   // classification branch of get_fixed_flag (MeshSmoother.cpp:293-340)
   std::pair<bool, int> geometry_fixed_flag(MeshGeometry* geom, size_t node) {
     if (!geom) return std::make_pair(false, (int)MS_VOLUME);
@@ -614,9 +643,58 @@ class ReferenceMeshSmootherConjugateGradientImpl : public ReferenceMeshSmootherB
     return pms_check_convergence(&st, gradNorm) != 0;
   }
 
-  // line_search + CG step are one C-ABI call; the state scalars are mirrored in and out
+  /// line_search(restarted, mfac_mult) (ReferenceMeshSmootherConjugateGradient.hpp:155, Def.hpp:466-591): the accepted
+  /// step length along cg_s; does not move the nodes.
+  Double line_search(bool& restarted, double mfac_mult = 1.0) {
+    if (dispatch_virtuals()) return line_search_host(restarted, mfac_mult);
+    sync_options();
+    pms_state st;
+    to_state(st);
+    int r = 0;
+    double a = 0;
+    check(ctx(), pms_line_search(ctx(), &st, mfac_mult, &r, &a));
+    from_state(st);
+    if (r) restarted = true;
+    return a;
+  }
+
+  /// metric(element, valid) (ReferenceMeshSmootherConjugateGradient.hpp:169): the current stage's metric of one element.
+  /// The device evaluates every element in one pass (there is no per-element host arithmetic); use
+  /// pms_get_element_metrics directly for bulk access.
+  virtual Double metric(size_t element, bool& valid) {
+    sync_options();
+    check(ctx(), pms_set_option(ctx(), "keep_element_metrics", 1.0));
+    double m = 0;
+    size_t n = 0;
+    check(ctx(), pms_total_metric(ctx(), m_stage, 0.0, &m, &n));
+    size_t ne = 0;
+    check(ctx(), pms_num_elements_local(ctx(), &ne));
+    std::vector<double> em(ne);
+    std::vector<int32_t> ef(ne);
+    check(ctx(), pms_get_element_metrics(ctx(), em.data(), ef.data()));
+    check(ctx(), pms_set_option(ctx(), "keep_element_metrics", 0.0));
+    if (element >= ne) throw std::runtime_error("metric: element out of range");
+    valid = ef[element] == 0;
+    return em[element];
+  }
+  /// nodal_edge_length_ave(node) (…ConjugateGradient.hpp:173, Def.hpp:39-65): mean over the node's elements of their mean
+  /// edge length on the reference mesh = the node's cg_edge_length after get_edge_lengths().
+  Double nodal_edge_length_ave(size_t node) {
+    get_edge_lengths(m_eMesh);
+    const size_t N = m_eMesh->num_nodes_local();
+    std::vector<double> el(N);
+    m_eMesh->get_field("cg_edge_length", el.data());
+    if (node >= N) throw std::runtime_error("nodal_edge_length_ave: node out of range");
+    return el[node];
+  }
+
+  // The exact class runs an iteration as ONE C-ABI call (line search, CG update and the fused passes stay on the device
+  // side of the boundary).  A class DERIVED from this one may override get_gradient / total_metric /
+  // update_node_positions / check_convergence, so for it the reference's control flow runs here on the host and calls
+  // those virtuals, exactly as Def.hpp:1010-1093 / :466-591 / ReferenceMeshSmootherBase.cpp:240-334 do.
   virtual double run_one_iteration() {  // Def.hpp:1010-1093
     sync_options();
+    if (dispatch_virtuals()) return run_one_iteration_host();
     pms_state st;
     to_state(st);
     double metric = 0;
@@ -627,13 +705,147 @@ class ReferenceMeshSmootherConjugateGradientImpl : public ReferenceMeshSmootherB
 
   virtual void run_algorithm() {  // ReferenceMeshSmootherBase.cpp:240-334 (writes smootherlog<in_filename>.txt)
     sync_options();
+    if (dispatch_virtuals()) return run_algorithm_host();
     pms_state st;
     int rc = pms_run_algorithm(ctx(), innerIter, gradNorm, this->m_log_name.c_str(), &st);
     from_state(st);
     check(ctx(), rc);
   }
 
- private:
+ protected:
+  bool dispatch_virtuals() const { return typeid(*this) != typeid(ReferenceMeshSmootherConjugateGradientImpl<MeshType>); }
+
+  Double line_search_host(bool& restarted, double mfac_mult) {  // Def.hpp:466-591 through the virtuals
+    const Double alpha_fac = 10.0, tau = 0.5, c0 = 1.e-1, min_alpha_factor = 1.e-12;
+    PerceptMesh* eMesh = m_eMesh;
+    m_alpha_0 = get_alpha_0();
+    Double alpha = alpha_fac * m_alpha_0;
+    bool total_valid = false;
+    size_t n_invalid = 0;
+    const Double metric_0 = total_metric(0.0, 1.0, total_valid, &n_invalid);
+    Double metric = 0.0;
+    Double sDotGrad = eMesh->nodal_field_dot("cg_s", "cg_g");
+    if (sDotGrad >= 0.0) {
+      eMesh->copy_field("cg_s", "cg_r");
+      m_alpha_0 = get_alpha_0();
+      alpha = alpha_fac * m_alpha_0;
+      sDotGrad = eMesh->nodal_field_dot("cg_s", "cg_g");
+      restarted = true;
+    }
+    if (!(sDotGrad < 0.0)) throw std::runtime_error("bad sDotGrad");
+    const Double armijo_offset_factor = c0 * sDotGrad;
+    bool converged = false;
+    total_valid = false;
+    const int niter = 1000;
+    for (int pass = 0; pass < 2 && !converged; pass++) {
+      if (pass == 1) {  // second chance along the steepest-descent direction, Def.hpp:515-554
+        restarted = true;
+        eMesh->copy_field("cg_s", "cg_r");
+        m_alpha_0 = get_alpha_0();
+        alpha = alpha_fac * m_alpha_0;
+        sDotGrad = eMesh->nodal_field_dot("cg_s", "cg_g");
+        if (!(sDotGrad < 0.0)) throw std::runtime_error("bad sDotGrad 2nd time");
+      }
+      for (int liter = 0; !converged && liter < niter; ++liter) {
+        metric = total_metric(alpha, 1.0, total_valid, &n_invalid);
+        const Double mfac = alpha * armijo_offset_factor * mfac_mult;
+        converged = (metric < metric_0 + mfac);
+        if (m_untangled) {
+          converged = converged && total_valid;
+          if (pass == 1 && total_valid && m_dmax_relative < gradNorm) converged = true;
+        }
+        if (!converged) alpha *= tau;
+        if (alpha < min_alpha_factor * m_alpha_0) break;
+      }
+    }
+    if (!converged) throw std::runtime_error("can't reduce metric");
+    const Double a1 = alpha / 2., a2 = alpha;
+    const Double f0 = metric_0, f1 = total_metric(a1, 1.0, total_valid), f2 = total_metric(a2, 1.0, total_valid);
+    const Double den = 2. * (a2 * (-f0 + f1) + a1 * (f0 - f2));
+    const Double num = a2 * a2 * (f1 - f0) + a1 * a1 * (f0 - f2);
+    if (std::fabs(den) > 1.e-10) {
+      const Double alpha_quadratic = num / den;
+      if (alpha_quadratic > 1.e-10 && alpha_quadratic < 2 * alpha) {
+        const Double fm = total_metric(alpha_quadratic, 1.0, total_valid);
+        if (fm < f2 && (m_stage == 0 || total_valid)) alpha = alpha_quadratic;
+      }
+    }
+    return alpha;
+  }
+
+  double run_one_iteration_host() {  // Def.hpp:1010-1093 through the virtuals
+    PerceptMesh* eMesh = m_eMesh;
+    bool total_valid = false;
+    if (m_num_nodes == 0) m_num_nodes = (size_t)eMesh->get_number_nodes();
+    if (m_iter == 0) {
+      get_edge_lengths(eMesh);
+      eMesh->nodal_field_set_value("cg_r", 0.0);
+      eMesh->nodal_field_set_value("cg_d", 0.0);
+      eMesh->nodal_field_set_value("cg_s", 0.0);
+    }
+    get_gradient();
+    eMesh->nodal_field_axpby(-1.0, "cg_g", 0.0, "cg_r");
+    m_dold = eMesh->nodal_field_dot("cg_d", "cg_d");
+    m_dmid = eMesh->nodal_field_dot("cg_r", "cg_d");
+    m_dnew = eMesh->nodal_field_dot("cg_r", "cg_r");
+    if (m_iter == 0) m_d0 = m_dnew;
+    const Double metric_check = total_metric(0.0, 1.0, total_valid);
+    m_total_metric = metric_check;
+    if (check_convergence() || metric_check == 0.0) return total_metric(0.0, 1.0, total_valid);
+    Double cg_beta = 0.0;
+    if (m_dold == 0.0)
+      cg_beta = 0.0;
+    else if (m_iter > 0)
+      cg_beta = (m_dnew - m_dmid) / m_dold;
+    const size_t N = m_num_nodes;
+    if (m_iter % N == 0 || cg_beta <= 0.0)
+      eMesh->copy_field("cg_s", "cg_r");
+    else
+      eMesh->nodal_field_axpby(1.0, "cg_r", cg_beta, "cg_s");
+    eMesh->copy_field("cg_d", "cg_r");
+    bool restarted = false;
+    const Double alpha = line_search(restarted);
+    const Double snorm = eMesh->nodal_field_dot("cg_s", "cg_s");
+    m_grad_norm_scaled = m_alpha_0 * std::sqrt(snorm) / Double(m_num_nodes);
+    m_alpha = alpha;
+    update_node_positions(alpha);
+    if (eMesh->get_smooth_surfaces()) {
+      snap_nodes();
+      if (m_stage != 0) {
+        bool total_valid_0 = true;
+        total_metric(0.0, 1.0, total_valid_0);
+        if (!total_valid_0) throw std::runtime_error("bad mesh after snap_node_positions...");
+      }
+    }
+    return total_metric(0.0, 1.0, total_valid);
+  }
+
+  void run_algorithm_host() {  // ReferenceMeshSmootherBase.cpp:240-334 through the virtuals (no log file on this path)
+    PerceptMesh* eMesh = m_eMesh;
+    m_num_nodes = (size_t)eMesh->get_number_nodes();
+    eMesh->copy_field("coordinates_lagged", "coordinates_NM1");
+    eMesh->nodal_field_axpbypgz(1.0, "coordinates_N", 0.0, "coordinates_NM1", 0.0, "coordinates");
+    m_num_invalid = Base::parallel_count_invalid_elements(eMesh);
+    m_untangled = (m_num_invalid == 0);
+    const int nstage = this->get_num_stages();
+    for (int stage = 0; stage < nstage; stage++) {
+      m_stage = stage;
+      if (stage != 0 && Base::parallel_count_invalid_elements(eMesh) != 0)
+        throw std::runtime_error("Invalid elements exist for start of stage 2, quiting");
+      for (int iter = 0; iter < innerIter; ++iter) {
+        m_iter = iter;
+        m_num_invalid = Base::parallel_count_invalid_elements(eMesh);
+        if (!m_untangled && m_num_invalid == 0) m_untangled = true;
+        m_global_metric = this->run_one_iteration();
+        const bool conv = this->check_convergence();
+        if (!m_untangled && m_num_invalid == 0) m_untangled = true;
+        if (conv && m_untangled) break;
+      }
+    }
+    eMesh->copy_field("coordinates_lagged", "coordinates");
+  }
+
+ protected:
   pms_ctx* ctx() const { return m_eMesh->ctx(); }
   void sync_options() { check(ctx(), pms_set_option(ctx(), "use_ref_mesh", m_use_ref_mesh ? 1.0 : 0.0)); }
   void to_state(pms_state& st) {

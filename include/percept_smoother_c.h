@@ -199,6 +199,11 @@ typedef struct pms_state {
 int pms_state_init(pms_ctx* ctx, pms_state* st);
 /* run_one_iteration (Def.hpp:1010-1093) incl. line_search (Def.hpp:466-591).    */
 int pms_run_one_iteration(pms_ctx* ctx, pms_state* st, double grad_norm, double* metric_out);
+/* line_search(bool& restarted, double mfac_mult) (Def.hpp:466-591;
+ * ReferenceMeshSmootherConjugateGradient.hpp:155) on its own: Armijo back-tracking from 10*alpha_0 along cg_s with the
+ * restart rules and the final quadratic fit; reads cg_s, cg_g, cg_r, cg_edge_length and st->stage/untangled/dmax_relative,
+ * returns the accepted step length, does not move the nodes (the caller follows with pms_update_node_positions).     */
+int pms_line_search(pms_ctx* ctx, pms_state* st, double mfac_mult, int* restarted, double* alpha);
 /* check_convergence (Def.hpp:989-1008).                                         */
 int pms_check_convergence(const pms_state* st, double grad_norm);
 /* run_algorithm (ReferenceMeshSmootherBase.cpp:240-334): both stages, writes the
@@ -251,6 +256,9 @@ enum { PMS_SURF_PLANE = 0, PMS_SURF_SPHERE = 1, PMS_SURF_CYLINDER = 2 };
 int pms_add_analytic_surface(pms_ctx* ctx, int kind, const double* params, int* surface_id);
 int pms_set_node_classification(pms_ctx* ctx, const int8_t* dof, const int32_t* surface_id);
 int pms_snap_nodes(pms_ctx* ctx, double* dmax);
+/* snap_to(node, coordinate, reset) (MeshSmoother.hpp:79, MeshSmoother.cpp:517-563): the node is put at xyz and snapped to
+ * its surface, xyz returns the snapped position; reset != 0 restores the node's coordinates afterwards.            */
+int pms_snap_point(pms_ctx* ctx, size_t node, double* xyz, int reset);
 int pms_get_surface_normals(pms_ctx* ctx, double* host_out);
 
 /* ---- structured 2x refinement feeding the smoother -------------------------------------------------

@@ -1096,7 +1096,7 @@ struct Smoother {
   }
 
   // line_search, Def.hpp:466-591
-  Real line_search(bool& restarted) {
+  Real line_search(bool& restarted, const Real mfac_mult = 1.0) {
     const Real alpha_fac = 10.0, tau = 0.5, c0 = 1.e-1, min_alpha_factor = 1.e-12;
     m_alpha_0 = get_alpha_0();
     Real alpha = alpha_fac * m_alpha_0;
@@ -1119,7 +1119,7 @@ struct Smoother {
     int liter = 0, niter = 1000;
     while (!converged && liter < niter) {
       metric = tm(alpha, total_valid, &n_invalid);
-      const Real mfac = alpha * armijo_offset_factor * Real(1.0);
+      const Real mfac = alpha * armijo_offset_factor * mfac_mult;
       converged = (metric < metric_0 + mfac);
       if (m_untangled) converged = converged && total_valid;
       if (!converged) {
@@ -1140,7 +1140,7 @@ struct Smoother {
     liter = 0;
     while (!converged && liter < niter) {
       metric = tm(alpha, total_valid);
-      const Real mfac = alpha * armijo_offset_factor;
+      const Real mfac = alpha * armijo_offset_factor * mfac_mult;
       converged = (metric < metric_0 + mfac);
       if (m_untangled) {
         converged = converged && total_valid;
@@ -1827,6 +1827,23 @@ int orc_run_one_iteration(orc_ctx* c, orc_state* st, double grad_norm, double* m
     s.m_global_metric = *metric_out;
     state_to(s, st);
   }
+  ORC_CATCH
+}
+// line_search(bool& restarted, double mfac_mult) on its own (ReferenceMeshSmootherConjugateGradient.hpp:155, Def.hpp:466-591)
+int orc_line_search(orc_ctx* c, orc_state* st, double mfac_mult, int* restarted, double* alpha) {
+  ORC_TRY bool r = false;
+  if (c->real_is_double) {
+    Smoother<double> s(*c);
+    state_from(s, st);
+    *alpha = s.line_search(r, mfac_mult);
+    state_to(s, st);
+  } else {
+    Smoother<LD> s(*c);
+    state_from(s, st);
+    *alpha = (double)s.line_search(r, (LD)mfac_mult);
+    state_to(s, st);
+  }
+  if (restarted) *restarted = r ? 1 : 0;
   ORC_CATCH
 }
 int orc_run_algorithm(orc_ctx* c, int inner_iterations, double grad_norm, const char* log_path, orc_state* st) {

@@ -79,6 +79,7 @@ class Api:
         "get_element_metrics": [C.c_void_p, C.c_void_p],
         "state_init": [C.POINTER(State)],
         "run_one_iteration": [C.POINTER(State), C.c_double, _dp],
+        "line_search": [C.POINTER(State), C.c_double, C.POINTER(C.c_int), _dp],
         "run_algorithm": [C.c_int, C.c_double, C.c_char_p, C.POINTER(State)],
         "add_analytic_surface": [C.c_int, _dp, C.POINTER(C.c_int)],
         "set_node_classification": [C.c_void_p, C.c_void_p],
@@ -96,6 +97,7 @@ class Api:
         "total_metric_multi": [C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_size_t)],
         "field_device_ptr": [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
         "field_release_ptr": [C.c_char_p],
+        "snap_point": [C.c_size_t, _dp, C.c_int],
         "comm_init": [C.c_void_p, C.c_int, C.c_int],
         "set_halo": [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         "halo_exchange": [C.c_char_p],
@@ -387,6 +389,18 @@ class Ctx:
         m = C.c_double()
         self._call("run_one_iteration", C.byref(st), float(grad_norm), C.byref(m))
         return m.value
+
+    def line_search(self, st, mfac_mult=1.0):
+        """line_search(restarted, mfac_mult) on its own -> (alpha, restarted); the nodes stay where they are."""
+        r, a = C.c_int(0), C.c_double()
+        self._call("line_search", C.byref(st), float(mfac_mult), C.byref(r), C.byref(a))
+        return a.value, bool(r.value)
+
+    def snap_point(self, node, xyz, reset=False):
+        """snap_to(node, coordinate, reset): returns the snapped position."""
+        v = (C.c_double * 3)(*xyz)
+        self._call("snap_point", int(node), v, 1 if reset else 0)
+        return [v[0], v[1], v[2]]
 
     def run_algorithm(self, inner_iterations, grad_norm, log_path=None):
         st = State()

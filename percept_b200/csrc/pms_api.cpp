@@ -907,7 +907,8 @@ struct Driver {
 
   // line_search, Def.hpp:466-591
   bool moved = false;  // line_search already applied the accepted step (update_node_positions) and holds f'(x_new)
-  double line_search(bool& restarted) {
+  bool allow_move = true;  // false for the stand-alone pms_line_search, which must leave the coordinates alone
+  double line_search(bool& restarted, const double mfac_mult = 1.0) {
     moved = false;
     const double alpha_fac = 10.0, tau = 0.5, c0 = 1.e-1, min_alpha_factor = 1.e-12;
     st->alpha_0 = alpha0_of_s();
@@ -935,7 +936,7 @@ struct Driver {
       speculate(alpha, tau);
       spec_cur++;
       metric = tm(alpha, total_valid, &n_invalid);
-      const double mfac = alpha * armijo_offset_factor * 1.0;
+      const double mfac = alpha * armijo_offset_factor * mfac_mult;
       converged = (metric < metric_0 + mfac);
       if (st->untangled) converged = converged && total_valid;
       if (!converged) {
@@ -958,7 +959,7 @@ struct Driver {
       speculate(alpha, tau);
       spec_cur++;
       metric = tm(alpha, total_valid);
-      const double mfac = alpha * armijo_offset_factor;
+      const double mfac = alpha * armijo_offset_factor * mfac_mult;
       converged = (metric < metric_0 + mfac);
       if (st->untangled) {
         converged = converged && total_valid;
@@ -980,7 +981,7 @@ struct Driver {
     if (std::fabs(den) > 1.e-10) {
       const double alpha_quadratic = num / den;
       if (alpha_quadratic > 1.e-10 && alpha_quadratic < 2 * alpha) {
-        if (fuse_passes() && !c->smooth_surfaces) {
+        if (fuse_passes() && !c->smooth_surfaces && allow_move) {
           // The quadratic step is accepted almost always, and an accepted step is followed by the update and by the
           // fused metric+gradient pass at the new coordinates.  So move there first and let that pass provide fm;
           // only a rejected step costs extra (restore x from coordinates_lagged).
@@ -1989,6 +1990,38 @@ int pms_snap_nodes(pms_ctx* c, double* dmax) {
   PMS_CATCH
 }
 
+// MeshSmootherImpl::snap_to (MeshSmoother.cpp:517-563): put the node at xyz, snap it to its surface, return the snapped
+// position in xyz; reset != 0 restores the node's coordinates afterwards.
+int pms_snap_point(pms_ctx* c, size_t node, double* xyz, int reset) {
+  PMS_TRY
+  require_committed(c);
+  if (!xyz || (long long)node >= c->N) throw PmsError(PMS_ERR_ARG, "bad node / null coordinate");
+  if (c->h_node_dof.empty() || c->h_node_dof[node] != 2 || c->h_node_surf[node] < 0) return PMS_OK;  // not on a surface: unchanged
+  DField& X = c->field("coordinates");
+  double save[3];
+  for (int r = 0; r < 3; r++) {
+    PMS_CUDA(cudaMemcpyAsync(&save[r], X.d + r * c->Npad + node, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PMS_CUDA(cudaMemcpyAsync(X.d + r * c->Npad + node, &xyz[r], sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  const int32_t hn = (int32_t)node, hs = c->h_node_surf[node];
+  int32_t* dn = dalloc<int32_t>(2);
+  PMS_CUDA(cudaMemcpyAsync(dn, &hn, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  PMS_CUDA(cudaMemcpyAsync(dn + 1, &hs, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  {
+    Timed t(c, FAM_UPDATE);
+    c->L->surf_snap(c->stream, 1, dn, dn + 1, c->d_surfaces, X.d, c->Npad, c->R, 0);
+    check_launch(c, "surf_snap");
+  }
+  for (int r = 0; r < 3; r++) PMS_CUDA(cudaMemcpyAsync(&xyz[r], X.d + r * c->Npad + node, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+  if (reset)
+    for (int r = 0; r < 3; r++) PMS_CUDA(cudaMemcpyAsync(X.d + r * c->Npad + node, &save[r], sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  PMS_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(dn);
+  X.version++;
+  PMS_CATCH
+}
+
 int pms_get_surface_normals(pms_ctx* c, double* host_out) {
   PMS_TRY
   require_committed(c);
@@ -2198,6 +2231,20 @@ int pms_run_one_iteration(pms_ctx* c, pms_state* st, double grad_norm, double* m
   const double m = d.run_one_iteration();
   st->global_metric = m;
   if (metric_out) *metric_out = m;
+  PMS_CATCH
+}
+
+// line_search (Def.hpp:466-591) on its own: needs cg_s (search direction), cg_g (gradient at the current coordinates),
+// cg_r (the restart direction) and cg_edge_length; leaves the coordinates where they are.
+int pms_line_search(pms_ctx* c, pms_state* st, double mfac_mult, int* restarted, double* alpha) {
+  PMS_TRY
+  require_committed(c);
+  if (!st || !alpha) throw PmsError(PMS_ERR_ARG, "null argument");
+  Driver d(c, st, 0.0);
+  d.allow_move = false;
+  bool r = false;
+  *alpha = d.line_search(r, mfac_mult);
+  if (restarted) *restarted = r ? 1 : 0;
   PMS_CATCH
 }
 

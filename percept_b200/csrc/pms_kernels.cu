@@ -592,6 +592,9 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
   int conn_nn[8];
   bool act_nn = false;
   long long e_nn = 0;
+  // ownership flag of the element (multi-GPU: ghost elements are evaluated but not counted), fetched with the
+  // connectivity two elements ahead: read at the point of use it cost a full memory latency per element (+11 % at N > 1)
+  uint8_t own_nn = 1, own_nxt = 1, own_cur = 1;
 
   auto load_conn = [&](long long tile) {  // connectivity of the element after next
     act_nn = false;
@@ -601,6 +604,7 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
       if (act_nn) {
 #pragma unroll
         for (int a = 0; a < NN; a++) conn_nn[a] = __ldg(&m.conn[(long long)a * m.conn_stride + e_nn]);
+        if (m.elem_owned) own_nn = __ldg(&m.elem_owned[e_nn]);
       }
     }
   };
@@ -611,6 +615,7 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
     } else {
       act_nxt = act_nn;
       e_nxt = e_nn;
+      own_nxt = own_nn;
     }
     if (act_nxt) {
       const long long sj = m.ni, sk = (long long)m.ni * m.nj;
@@ -642,6 +647,7 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
     e_cur = e_nxt;
     act_cur = act_nxt;
     bits_cur = bits_nxt;
+    own_cur = own_nxt;
     cp_async_wait_all();
     const int cur = buf;  // buffer holding the current element
     double vc[8][3], vo[8][3];
@@ -689,8 +695,7 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
 #pragma unroll
         for (int r = 0; r < 3; r++) eg[(long long)(a * 3 + r) * eg_stride + ge] = use ? grad[vpos<FL, FAST>(a)][r] : 0.0;
     }
-    bool counted = true;
-    if (FL != FL_SGRID && m.elem_owned) counted = m.elem_owned[e_cur] != 0;
+    const bool counted = FL == FL_SGRID || own_cur != 0;
     if (counted) {
       val[0] += mm;
       inv += valid ? 0 : 1;
@@ -1201,6 +1206,8 @@ __global__ void __launch_bounds__(NTP, MULTI_MINB) k_metric_multi(const MeshDev 
       }
     }
     const unsigned bits = m.elem_fixed_bits[m.elem_off + e];
+    bool counted = true;  // (loaded here, beside the vertex gather, not at its use after the evaluation)
+    if (FL != FL_SGRID && m.elem_owned) counted = __ldg(&m.elem_owned[e]) != 0;
     cp_async_commit();
     cp_async_wait_all();
 #pragma unroll
@@ -1212,8 +1219,6 @@ __global__ void __launch_bounds__(NTP, MULTI_MINB) k_metric_multi(const MeshDev 
     // (measured alternatives, both slower: reloading accessors SmemVertsReload without spills at 2 CTAs/SM 4.30 ms, or at
     //  168 registers / 3 CTAs/SM 4.61 ms, vs 3.63 ms for 8 alphas at 256^3 with the values kept in registers)
     const SmemVerts<FL == FL_HEX8, NTP> VC(slot_in(0, 0, 0)), VO(slot_in(1, 0, 0)), VS(slot_in(2, 0, 0));
-    bool counted = true;
-    if (FL != FL_SGRID && m.elem_owned) counted = m.elem_owned[e] != 0;
     double es[NB];
 #pragma unroll
     for (int k = 0; k < NB; k++) es[k] = 0.0;

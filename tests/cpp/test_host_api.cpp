@@ -221,6 +221,93 @@ int main() {
                 (double)sm.m_global_metric, off_surface);
     std::remove("smootherlogcurved_box.txt");
   }
+  {  // the virtual members are live: a class derived from the smoother that overrides total_metric / get_gradient /
+     // update_node_positions sees them called by run_one_iteration() and line_search() (Def.hpp:1010-1093, :466-591),
+     // and gets the same iterates as the exact class (which runs an iteration as one C call)
+    struct Counting : ReferenceMeshSmootherConjugateGradientImpl<StructuredGrid> {
+      using ReferenceMeshSmootherConjugateGradientImpl<StructuredGrid>::ReferenceMeshSmootherConjugateGradientImpl;
+      int n_metric = 0, n_grad = 0, n_update = 0;
+      Double total_metric(Double alpha, double scale, bool& valid, size_t* num_invalid = 0) override {
+        n_metric++;
+        return ReferenceMeshSmootherConjugateGradientImpl<StructuredGrid>::total_metric(alpha, scale, valid, num_invalid);
+      }
+      void get_gradient() override {
+        n_grad++;
+        ReferenceMeshSmootherConjugateGradientImpl<StructuredGrid>::get_gradient();
+      }
+      void update_node_positions(Double alpha) override {
+        n_update++;
+        ReferenceMeshSmootherConjugateGradientImpl<StructuredGrid>::update_node_positions(alpha);
+      }
+    };
+    const unsigned nele = 12;
+    std::vector<double> xa, xb;
+    Double ma = 0, mb = 0;
+    for (int derived = 0; derived < 2; derived++) {
+      PerceptMesh eMesh(3u);
+      build_perturbed_cube(eMesh, nele);
+      const size_t N = eMesh.num_nodes_local();
+      std::vector<double> x(3 * N);
+      eMesh.get_field("coordinates_NM1", x.data());
+      pms_fixture_perturb_rand(nele + 1, nele + 1, nele + 1, 0.3 / (double)nele, 1, x.data());  // a valid start
+      eMesh.set_field("coordinates", x.data());
+      eMesh.set_field("coordinates_N", x.data());
+      eMesh.setProperty("in_filename", "virtuals");
+      SGridBoundarySelector boundarySelector(&eMesh);
+      if (derived) {
+        Counting sm(&eMesh, NULL, &boundarySelector, 0, 4, 0.0, 1);
+        sm.run();
+        EXPECT_EQ(sm.n_grad >= 8, true);       // one gradient per CG iteration, two stages
+        EXPECT_EQ(sm.n_metric > sm.n_grad, true);  // the line search's trials went through the override
+        EXPECT_EQ(sm.n_update >= 4, true);
+        mb = sm.m_global_metric;
+        // line_search on its own: a descent step along -g that lowers the metric and leaves the nodes where they are
+        sm.m_stage = 1;
+        sm.get_gradient();
+        eMesh.nodal_field_axpby(-1.0, "cg_g", 0.0, "cg_r");
+        eMesh.copy_field("cg_s", "cg_r");
+        std::vector<double> before(3 * N), after(3 * N);
+        eMesh.get_field("coordinates", before.data());
+        bool restarted = false, valid = true;
+        const int nm0 = sm.n_metric;
+        const Double alpha = sm.line_search(restarted, 1.0);
+        eMesh.get_field("coordinates", after.data());
+        EXPECT_EQ(alpha > 0.0, true);
+        EXPECT_EQ(sm.n_metric > nm0, true);
+        EXPECT_EQ(before == after, true);
+        EXPECT_EQ(sm.total_metric(alpha, 1.0, valid) <= sm.total_metric(0.0, 1.0, valid), true);
+        xb.resize(3 * N);
+        eMesh.get_field("coordinates", xb.data());
+        std::printf("virtual dispatch: %d total_metric, %d get_gradient, %d update_node_positions calls; line_search alpha %.3e\n",
+                    sm.n_metric, sm.n_grad, sm.n_update, (double)alpha);
+      } else {
+        ReferenceMeshSmootherConjugateGradientImpl<StructuredGrid> sm(&eMesh, NULL, &boundarySelector, 0, 4, 0.0, 1);
+        sm.run();
+        ma = sm.m_global_metric;
+        // the exact class: line_search through pms_line_search, same contract
+        sm.m_stage = 1;
+        sm.get_gradient();
+        eMesh.nodal_field_axpby(-1.0, "cg_g", 0.0, "cg_r");
+        eMesh.copy_field("cg_s", "cg_r");
+        bool restarted = false;
+        const Double alpha = sm.line_search(restarted, 1.0);
+        EXPECT_EQ(alpha > 0.0, true);
+        xa.resize(3 * N);
+        eMesh.get_field("coordinates", xa.data());
+        // helpers of the reference's public surface
+        bool valid = false;
+        const Double m_el = sm.metric((size_t)0, valid);
+        EXPECT_EQ(valid, true);
+        EXPECT_EQ(m_el >= 0.0, true);
+        EXPECT_NEAR(sm.nodal_edge_length_ave((size_t)(N / 2)), 1.0 / nele, 1e-12);
+      }
+      std::remove("smootherlogvirtuals.txt");
+    }
+    double maxd = 0;
+    for (size_t i = 0; i < xa.size(); i++) maxd = std::fmax(maxd, std::fabs(xa[i] - xb[i]));
+    EXPECT_NEAR(maxd, 0.0, 1e-9);
+    EXPECT_NEAR(mb, ma, 1e-9 * std::fabs((double)ma));
+  }
   {  // error convention: failures surface as std::runtime_error
     bool threw = false;
     try {

@@ -560,3 +560,35 @@ def test_edge_cases_behave_like_the_reference(kind):
     g.get_gradient(1)
     gg = g.download("cg_g")
     assert np.all(np.abs(gg.sum(axis=1)) <= 1e-10 * np.abs(gg).sum(axis=1))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("strict", [0, 1])
+def test_line_search_on_its_own(kind, strict):
+    """pms_line_search = line_search(bool& restarted, double mfac_mult) (ReferenceMeshSmootherConjugateGradient.hpp:155,
+    Def.hpp:466-591): same accepted step length as the oracle, nodes left where they are; a larger mfac_mult demands a
+    larger decrease, so the accepted step cannot grow."""
+    g, o = pair(kind, 10, 0.25, strict)
+    for c in (g, o):
+        c.set_option("cache_metric", 1)
+        c.get_edge_lengths()
+        c.get_gradient(1)
+        c.axpby(-1.0, "cg_g", 0.0, "cg_r")
+        c.copy_field("cg_s", "cg_r")
+    x0 = g.download("coordinates").copy()
+    out = []
+    for mult in (1.0, 4.0):
+        sg, so = g.state_init(), o.state_init()
+        for st in (sg, so):
+            st.stage, st.untangled = 1, 1
+        ag, rg = g.line_search(sg, mult)
+        ao, ro = o.line_search(so, mult)
+        assert rg == ro
+        assert abs(ag - ao) <= 1e-9 * abs(ao)
+        assert abs(sg.alpha_0 - so.alpha_0) <= 1e-12 * so.alpha_0
+        out.append(ag)
+    assert out[1] <= out[0]
+    assert np.array_equal(g.download("coordinates"), x0)
+    m0, _ = g.total_metric(1, 0.0)
+    m1, _ = g.total_metric(1, out[0])
+    assert m1 < m0
