@@ -257,7 +257,7 @@ int main() {
       if (derived) {
         Counting sm(&eMesh, NULL, &boundarySelector, 0, 4, 0.0, 1);
         sm.run();
-        EXPECT_EQ(sm.n_grad >= 8, true);       // one gradient per CG iteration, two stages
+        EXPECT_EQ(sm.n_grad >= 5, true);       // one gradient per CG iteration (stage 0 stops early on a valid mesh, stage 1 runs its 4)
         EXPECT_EQ(sm.n_metric > sm.n_grad, true);  // the line search's trials went through the override
         EXPECT_EQ(sm.n_update >= 4, true);
         mb = sm.m_global_metric;
