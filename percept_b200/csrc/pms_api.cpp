@@ -263,6 +263,7 @@ void interface_sum(pms_ctx* c, DField& F);
 
 // total_metric(alpha), Def.hpp:330-388, without materialising x + alpha*s
 void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t* ninv, bool count_eval = true) {
+  pms_fast::set_variant(c->var_metric, c->var_grad);  // the variant switches live in the kernel TU: apply this ctx's
   DField& X = c->field("coordinates");
   DField& S = c->field("cg_s");
   DField& W = c->field("coordinates_NM1");
@@ -581,6 +582,7 @@ void ensure_eg(pms_ctx* c) {
 
 // get_gradient (Def.hpp:1481-1520); optionally the fused metric of the same pass
 void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write_r = true) {
+  pms_fast::set_variant(c->var_metric, c->var_grad);  // the variant switches live in the kernel TU: apply this ctx's
   DField& X = c->field("coordinates");
   DField& W = c->field("coordinates_NM1");
   DField& G = c->field("cg_g");
@@ -1344,6 +1346,13 @@ int pms_block_add_zone_connectivity(pms_ctx* c, int block, int donor, const int 
   PMS_TRY
   if (block < 0 || block >= (int)c->blocks.size() || donor < 0) throw PmsError(PMS_ERR_ARG, "bad block id");
   if (c->committed) throw PmsError(PMS_ERR_ARG, "mesh already committed");
+  // 1-based inclusive ranges inside the owner block (the donor side is checked at commit, when every block is known)
+  for (int d = 0; d < 3; d++) {
+    const int n = (int)c->blocks[block].n[d];
+    if (ob[d] < 1 || ob[d] > n || oe[d] < 1 || oe[d] > n)
+      throw PmsError(PMS_ERR_ARG, "zone connectivity: owner range outside the block's nodes");
+    if (std::abs(tr[d]) < 1 || std::abs(tr[d]) > 3) throw PmsError(PMS_ERR_ARG, "zone connectivity: transform entries must be +-1, +-2, +-3");
+  }
   HZone z;
   z.donor = donor;
   for (int d = 0; d < 3; d++) {
@@ -1482,7 +1491,14 @@ int pms_commit(pms_ctx* c) {
     c->topo = 8;
     for (auto& b : c->blocks)
       for (auto& z : b.zones)
+      {
         if (z.donor >= (int)c->blocks.size()) throw PmsError(PMS_ERR_ARG, "zone connectivity donor block does not exist");
+        for (int d = 0; d < 3; d++) {
+          const int n = (int)c->blocks[z.donor].n[d];
+          if (z.donor_beg[d] < 1 || z.donor_beg[d] > n || z.donor_end[d] < 1 || z.donor_end[d] > n)
+            throw PmsError(PMS_ERR_ARG, "zone connectivity: donor range outside the donor block's nodes");
+        }
+      }
   }
   if (c->N >= (1ll << 31)) throw PmsError(PMS_ERR_ARG, "more than 2^31 nodes per ctx");
   c->Npad = (c->N + 31) / 32 * 32;
@@ -1654,6 +1670,8 @@ int pms_commit(pms_ctx* c) {
     long long nb = m.kind == pmsk::KIND_SGRID
                        ? (long long)((m.ni + 30) / 32) * ((m.nj + 2) / 4) * ((m.nk + 0) / 2 + 1)
                        : (m.nelems + 255) / 256;
+    if (m.kind == pmsk::KIND_SGRID)  // the lane-cooperative variants (8 x 4 x 64 cell columns): larger grids on thin slabs
+      nb = std::max(nb, (long long)((m.ni + 6) / 8) * ((m.nj + 2) / 4) * ((m.nk + 62) / 64));
     maxb = std::max(maxb, nb + 8);
   }
   c->R.max_blocks = (int)maxb;
