@@ -576,6 +576,86 @@ void build_bricks(pms_ctx* c) {
   c->bricks_wv = W.version;
 }
 
+// Plan of the one-kernel unstructured gradient: slab length from the largest element-index span around a node, nodes
+// grouped by the slab of their last adjacent element (ascending node id inside a group), ring + counters.
+void build_ws_plan(pms_ctx* c) {
+  c->ws_failed = true;
+  int nsm = 0;
+  if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess || nsm < 1) return;
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+  if (!coop) return;
+  const long long E = c->E, N = c->N, nwarps = (long long)nsm * 8;
+  const int npe = c->topo == 4 ? 4 : 8;
+  long long span = 0;
+  for (long long n = 0; n < N; n++) {
+    const int64_t p0 = c->h_csr_ptr[n], p1 = c->h_csr_ptr[n + 1];
+    if (p1 > p0) span = std::max<long long>(span, (c->h_csr_ent[p1 - 1] >> 3) - (c->h_csr_ent[p0] >> 3));
+  }
+  const long long tpw = std::max<long long>(1, (span + 1 + 32 * nwarps - 1) / (32 * nwarps));
+  const long long slab = 32 * nwarps * tpw;
+  if (4 * slab >= E || tpw > (1 << 20)) return;  // the ring would be as large as the full scratch: keep the two-pass path
+  if (!c->d_csr_ent32 || 24 * 4 * slab >= (1ll << 31) || E * 8 >= (1ll << 31)) return;  // the gather's 32-bit index arithmetic
+  const long long ntiles = (E + 31) / 32, tps = nwarps * tpw;
+  const long long nslabs = (ntiles + tps - 1) / tps;
+  if (nslabs >= (1ll << 30)) return;
+  std::vector<long long> goff(nslabs + 1, 0);
+  std::vector<int32_t> grp(N);
+  for (long long n = 0; n < N; n++) {
+    const int64_t p0 = c->h_csr_ptr[n], p1 = c->h_csr_ptr[n + 1];
+    grp[n] = p1 > p0 ? (int32_t)((c->h_csr_ent[p1 - 1] >> 3) / slab) : 0;
+    goff[grp[n] + 1]++;
+  }
+  for (long long s = 0; s < nslabs; s++) goff[s + 1] += goff[s];
+  std::vector<int32_t> gnodes(N);
+  {
+    std::vector<long long> fill(goff.begin(), goff.end() - 1);
+    for (long long n = 0; n < N; n++) gnodes[fill[grp[n]]++] = (int32_t)n;
+  }
+  // gather table: the node's CSR walk resolved into ring offsets (an element of slab s sits in ring slot s % 4)
+  long long maxval = 0;
+  for (long long n = 0; n < N; n++) maxval = std::max<long long>(maxval, c->h_csr_ptr[n + 1] - c->h_csr_ptr[n]);
+  const long long tabw = std::max<long long>(4, (maxval + 3) / 4 * 4);
+  if (tabw > 64) return;  // (a node shared by more than 64 elements: keep the two-pass path)
+  const long long ring_elems = 4 * slab;
+  std::vector<int32_t> gtab((size_t)tabw * N, -1);
+  const unsigned nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  auto parallel_for = [&](long long n, const std::function<void(long long, long long)>& fn) {
+    std::vector<std::thread> th;
+    const long long chunk = (n + nthreads - 1) / nthreads;
+    for (unsigned t = 0; t < nthreads; t++) {
+      const long long a = t * chunk, b = std::min(n, a + chunk);
+      if (a < b) th.emplace_back(fn, a, b);
+    }
+    for (auto& x : th) x.join();
+  };
+  parallel_for(N, [&](long long qa, long long qb) {
+    for (long long q = qa; q < qb; q++) {
+      const long long n = gnodes[q];
+      const int64_t p0 = c->h_csr_ptr[n], p1 = c->h_csr_ptr[n + 1];
+      for (int64_t p = p0; p < p1; p++) {
+        const int64_t ent = c->h_csr_ent[p];
+        const long long e = ent >> 3, s = e / slab;
+        gtab[(size_t)(p - p0) * N + q] = (int32_t)((ent & 7) * 3 * ring_elems + (s % 4) * slab + (e - s * slab));
+      }
+    }
+  });
+  pmsk::WsPlanDev& P = c->ws;
+  P.gtab = dupload(gtab);
+  P.tab_w = (int)tabw;
+  P.tab_n = N;
+  P.slab_elems = slab;
+  P.tiles_per_warp = (int)tpw;
+  P.nslabs = (int)nslabs;
+  P.gnodes = dupload(gnodes);
+  P.goff = dupload(goff);
+  P.ring = dalloc<double>((size_t)3 * npe * 4 * slab);
+  P.counters = dalloc<int>((size_t)2 * nsm);
+  c->ws_grid = nsm;
+  c->ws_built = true;
+  c->ws_failed = false;
+}
+
 void ensure_eg(pms_ctx* c) {
   if (!c->d_eg) c->d_eg = dalloc<double>((size_t)3 * (c->topo == 4 ? 4 : 8) * c->Epad);
 }
@@ -608,6 +688,24 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write
         if (b > 0) throw PmsError(PMS_ERR_CUDA, "fused structured gradient refused a block after accepting another");
         c->launches -= 2;
         c->fam_launches[FAM_GRADIENT] -= 2;
+      }
+    }
+  }
+  if (!fused_ok && !c->structured && c->elem_ws && c->var_grad == 2 && !c->strict_fp && !c->keep_elem) {
+    if (!c->ws_built && !c->ws_failed) build_ws_plan(c);
+    if (c->ws_built) {
+      Timed t(c, FAM_GRADIENT, 1);
+      PMS_CUDA(cudaMemsetAsync(c->ws.counters, 0, (size_t)2 * c->ws_grid * sizeof(int), c->stream));
+      fused_ok = c->L->grad_ws(c->stream, c->dev_blocks[0], c->ws, c->ws_grid, stage, use_ref, X.d, W.d, c->Npad, c->d_fixed,
+                               c->d_node_owned, G.d, write_r ? Rr.d : nullptr, c->R, 0);
+      if (!fused_ok) {
+        cudaGetLastError();
+        c->ws_built = false;
+        c->ws_failed = true;  // (launch refused: not tried again)
+        c->launches--;
+        c->fam_launches[FAM_GRADIENT]--;
+      } else {
+        check_launch(c, "grad_ws");
       }
     }
   }
@@ -1246,7 +1344,7 @@ void pms_destroy(pms_ctx* c) {
                     c->d_csr_ptr,   c->d_csr_ent,   c->d_grp_ptr,    c->d_grp_nodes,  c->d_eg,       c->d_elem_metric,
                     c->d_elem_flag, c->R.partial_d, c->R.partial_u,  c->R.ticket,     c->R.out_d,    c->R.out_u,
                     c->d_send_nodes, c->d_recv_nodes, c->d_send_buf, c->d_recv_buf,   c->d_coll, c->d_skip, c->d_csr_ent32, c->d_if_nodes, c->d_sh_nodes, c->d_sh_cnt, c->d_sh_ptr, c->d_sh_pos,
-                    c->d_if_send, c->d_if_recv, c->d_seam};
+                    c->d_if_send, c->d_if_recv, c->d_seam, (void*)c->ws.gnodes, (void*)c->ws.goff, (void*)c->ws.gtab, c->ws.ring, c->ws.counters};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->h_out_d) cudaFreeHost(c->h_out_d);
@@ -1306,6 +1404,9 @@ int pms_set_option(pms_ctx* c, const char* key, double v) {
   } else if (k == "variant_grad_corners") {
     c->var_grad = (int)v;
     pms_fast::set_variant(c->var_metric, c->var_grad);
+    invalidate_cache(c);
+  } else if (k == "elem_ws") {  // 1: one-kernel unstructured gradient (element loop + lagged gather); 0 (default): two passes
+    c->elem_ws = v != 0;
     invalidate_cache(c);
   } else if (k == "sgrid_fused") {  // 1 (default): one-pass tile kernel for structured gradients; 0: element pass + gather
     c->sgrid_fused = v != 0;

@@ -77,6 +77,10 @@ struct pms_ctx {
   int64_t *d_grp_ptr = nullptr, *d_grp_nodes = nullptr;
   long long n_groups = 0;
   double* d_eg = nullptr;  // element-gradient scratch [3*npe][Epad]
+  // one-kernel unstructured gradient (pms_elem_ws.cuh)
+  pmsk::WsPlanDev ws{};
+  bool ws_built = false, ws_failed = false, elem_ws = false;  // (off by default: measured slower than the two passes)
+  int ws_grid = 0;
   double* d_seam = nullptr;  // tile-seam scratch of the fused structured gradient (pms_sgrid_tile.cuh)
   bool sgrid_fused = true;
   // brick tables of the scratch-free hex8 gradient (built lazily from the reference-mesh centroids)

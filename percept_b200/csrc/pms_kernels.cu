@@ -1579,6 +1579,7 @@ static void launch_grad_gather(cudaStream_t st, const MeshDev& m, const double* 
 }
 
 #include "pms_sgrid_tile.cuh"
+#include "pms_elem_ws.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // multi-block interface reconciliation: complete sum over all duplicates, ascending block id
@@ -2183,7 +2184,7 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_group_sum, launch_axpby,         launch_axpbypgz,    launch_set,
                                       launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_cg_s_update_dots, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,
-                                      launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_shared_sum,
+                                      launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_elem_ws, launch_shared_sum,
                                       launch_metric_multi, launch_refine_sgrid, launch_surf_project, launch_surf_snap, launch_surf_normals};
 
 const Launchers* launchers() { return &g_launchers; }

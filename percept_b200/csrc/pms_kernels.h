@@ -72,6 +72,22 @@ constexpr int BRICK_GTAB_BYTES = 16 + 8 * BRICK_MAX_NODES + 16 * BRICK_MAX_NODES
 constexpr int BRICK_EX_STRIDE = 25;
 constexpr int BRICK_EX_ZERO = BRICK_ELEMS * BRICK_EX_STRIDE;
 
+// plan of the one-kernel unstructured gradient (pms_elem_ws.cuh): slabs of elements in index order, nodes grouped by the
+// slab of their last adjacent element, a ring of 4 slabs of per-element contributions, cross-CTA progress counters
+struct WsPlanDev {
+  long long slab_elems;     // elements per slab = 32 * (compute warps of the grid) * tiles_per_warp
+  int tiles_per_warp;       // warp tiles each compute warp owns per slab
+  int nslabs;
+  const int32_t* gnodes;    // nodes sorted by (group, node id); group = slab of the node's last adjacent element
+  const long long* goff;    // [nslabs + 1]
+  const int32_t* gtab;      // [tab_w][tab_n]: ring offset (local node * 3 * ring_elems + ring index) of the k-th adjacent
+                            // element's contribution to the node at gnodes position q, ascending element order; -1 = none
+  int tab_w;                // entries per node (multiple of 4, >= the largest valence)
+  long long tab_n;          // = nnodes
+  double* ring;             // [3 * npe][4 * slab_elems]
+  int* counters;            // prog[grid] then gprog[grid] (per-CTA progress words), zeroed before the launch
+};
+
 // analytic stand-in for a MeshGeometry evaluator: 0 plane (p, unit normal u), 1 sphere (centre p, R),
 // 2 cylinder (axis point p, unit axis u, R)
 struct SurfaceDev {
@@ -145,6 +161,11 @@ struct Launchers {
   bool (*grad_bricks)(cudaStream_t, const MeshDev&, const BrickDev&, int stage, const double* x, const double* w,
                       long long stride, const uint8_t* fixed, const uint8_t* node_owned, double* g, double* r_out,
                       const Reduce&, int slot, double* elem_metric, int32_t* elem_flag);
+  // one-kernel unstructured metric + gradient (element loop + lagged node gather, ring scratch in L2); `grid` = the CTA
+  // count the plan was built for; returns false when unsupported (strict build) or the launch is refused
+  bool (*grad_ws)(cudaStream_t, const MeshDev&, const WsPlanDev&, int grid, int stage, int use_ref, const double* x,
+                  const double* w, long long stride, const uint8_t* fixed, const uint8_t* node_owned, double* g, double* r_out,
+                  const Reduce&, int slot);
   // cross-rank interface sum (structured block per GPU), ascending rank order
   void (*shared_sum)(cudaStream_t, long long nshared, const int32_t* nodes, const int64_t* ptr, const int64_t* ent_pos,
                      const int32_t* ent_cnt, const double* recvbuf, double* f, int ncomp, long long stride);
