@@ -263,7 +263,7 @@ void interface_sum(pms_ctx* c, DField& F);
 
 // total_metric(alpha), Def.hpp:330-388, without materialising x + alpha*s
 void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t* ninv, bool count_eval = true) {
-  pms_fast::set_variant(c->var_metric, c->var_grad);  // the variant switches live in the kernel TU: apply this ctx's
+  (c->strict_fp ? pms_strict::set_variant : pms_fast::set_variant)(c->var_metric, c->var_grad, c->sgrid_fused ? 1 : 0);  // the switches live in the kernel TU: apply this ctx's
   DField& X = c->field("coordinates");
   DField& S = c->field("cg_s");
   DField& W = c->field("coordinates_NM1");
@@ -311,7 +311,9 @@ bool op_total_metric_multi(pms_ctx* c, int stage, int nb, const double* alphas, 
   DField& W = c->field("coordinates_NM1");
   {
     Timed t(c, FAM_METRIC);
-    if (!c->L->metric_multi(c->stream, c->dev_blocks[0], stage, c->use_ref_mesh ? 1 : 0, nb, X.d, S.d, W.d, c->Npad, alphas, c->R, 0)) {
+    (c->strict_fp ? pms_strict::set_variant : pms_fast::set_variant)(c->var_metric, c->var_grad, c->sgrid_fused ? 1 : 0);
+    if (!c->L->metric_multi(c->stream, c->dev_blocks[0], stage, c->use_ref_mesh ? 1 : 0, nb, X.d, S.d, W.d, c->Npad, alphas, c->R, 0,
+                            c->d_fixed)) {
       c->launches--;
       c->fam_launches[FAM_METRIC]--;
       return false;
@@ -662,7 +664,7 @@ void ensure_eg(pms_ctx* c) {
 
 // get_gradient (Def.hpp:1481-1520); optionally the fused metric of the same pass
 void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write_r = true) {
-  pms_fast::set_variant(c->var_metric, c->var_grad);  // the variant switches live in the kernel TU: apply this ctx's
+  (c->strict_fp ? pms_strict::set_variant : pms_fast::set_variant)(c->var_metric, c->var_grad, c->sgrid_fused ? 1 : 0);  // the switches live in the kernel TU: apply this ctx's
   DField& X = c->field("coordinates");
   DField& W = c->field("coordinates_NM1");
   DField& G = c->field("cg_g");

@@ -22,6 +22,7 @@
 #define PMS_GRAD_VIA_GRAM 1
 #endif
 
+
 namespace pmsdev {
 
 PMS_DI double fast_rsqrt(double x) {
@@ -226,10 +227,12 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
 // The 8 coefficients cost about two single evaluations of the corner; each further alpha costs ~20 FP64 instructions
 // (two Horner forms, one rsqrt) instead of ~94.  vs must already be zero at fixed nodes (update_coordinates.cpp:255).
 // sum[k] += metric of this element at al[k]; bit k of invmask set when any corner has det A(al[k]) <= 0.
-template <int STAGE, int NB, class VC, class VS, class VO>
+template <int STAGE, int NB, int CORNER_UNROLL = 8, class VC, class VS, class VO>
 PMS_DI void hex_metric_multi(const VC& vc, const VS& vs, const VO& vo, const double (&al)[NB], double (&sum)[NB], unsigned& invmask) {
   invmask = 0;
-#pragma unroll
+  // CORNER_UNROLL < 8 keeps fewer corners' edge vectors and coefficients live (no spills), at the price of run-time
+  // vertex addressing; measured per kernel
+#pragma unroll CORNER_UNROLL
   for (int c = 0; c < 8; c++) {
     double a0[3], a1[3], a2[3], b0[3], b1[3], b2[3], w0[3], w1[3], w2[3];
     corner_edge<0>(vc, c, a0);

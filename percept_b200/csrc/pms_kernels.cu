@@ -38,6 +38,16 @@ constexpr int NT = 256;   // threads per block of the simple kernels
 constexpr int NTP = 128;  // threads per block of the pipelined / quad-lane element kernels
 constexpr int TBX = 32, TBY = 4, TBZ = 2;  // structured cell tile per block
 
+static int sm_count() {  // SMs of the current device (persistent grids are sized from it)
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+  }
+  return n;
+}
+
 // ------------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------------
@@ -721,7 +731,7 @@ static void launch_elem_pipe(cudaStream_t st, const MeshDev& m, const double* x,
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
   const long long nt = num_ptiles<FL>(m);
-  const long long cap = 148LL * blocks_per_sm;
+  const long long cap = (long long)sm_count() * blocks_per_sm;
   const unsigned grid = (unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap);
   kern<<<grid, NTP, smem, st>>>(m, x, s, w, stride, alpha, eg, egs, R, slot, em, ef);
 }
@@ -1160,6 +1170,9 @@ static void launch_metric_occ(cudaStream_t st, const MeshDev& m, const double* x
   kern<<<(unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), NTP, smem, st>>>(m, x, s, w, stride, alpha, R, slot);
 }
 
+int g_sgrid_tile = 1;  // structured blocks: 1 = TMA-staged tile kernels for the metric passes, 0 = per-thread pipelined kernels
+#include "pms_sgrid_tile.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // Multi-alpha hex metric: the line search's trial sequence alpha_init * tau^k is known before its outcomes are, so one
 // pass evaluates NB of them (hex_metric_multi: per-corner polynomial coefficients once, ~20 FP64 per extra alpha).
@@ -1256,7 +1269,7 @@ static void launch_metric_multi2(cudaStream_t st, const MeshDev& m, const double
   AlphaPack<NB> al;
   for (int k = 0; k < NB; k++) al.a[k] = alphas[k];
   const long long nt = num_ptiles<FL>(m);
-  long long cap = 148LL * blocks_per_sm;
+  long long cap = (long long)sm_count() * blocks_per_sm;
   if (cap > R.max_blocks) cap = R.max_blocks;
   kern<<<(unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), NTP, smem, st>>>(m, x, s, w, stride, al, R, slot);
 }
@@ -1269,8 +1282,13 @@ static void launch_metric_multi1(cudaStream_t st, const MeshDev& m, int stage, c
     launch_metric_multi2<FL, 1, NB>(st, m, x, s, w, stride, alphas, R, slot);
 }
 static bool launch_metric_multi(cudaStream_t st, const MeshDev& m, int stage, int use_ref, int nb, const double* x, const double* s,
-                                const double* w, long long stride, const double* alphas, const Reduce& R, int slot) {
+                                const double* w, long long stride, const double* alphas, const Reduce& R, int slot,
+                                const uint8_t* fixed) {
   if (STRICT || m.kind == KIND_TET4 || (stage != 0 && !use_ref) || (nb != 8 && nb != 12 && nb != 16)) return false;
+  // structured blocks: TMA-staged tile kernel (pms_sgrid_tile.cuh)
+  // (ShapeB1 only: the cheap untangle polynomial runs faster in the per-thread pipelined kernel, 1.73 vs 1.97 ms)
+  if (m.kind == KIND_SGRID && stage == 1 && g_sgrid_tile && launch_sgrid_tile_multi(st, m, stage, nb, x, s, w, stride, fixed, alphas, R, slot))
+    return true;
   if (m.kind == KIND_SGRID) {
     if (nb == 8)
       launch_metric_multi1<FL_SGRID, 8>(st, m, stage, x, s, w, stride, alphas, R, slot);
@@ -1347,6 +1365,9 @@ template <int FL, int STAGE, bool USE_REF>
 static void launch_metric2(cudaStream_t st, const MeshDev& m, const double* x, const double* s, const double* w,
                            long long stride, double alpha, const Reduce& R, int slot, double* em, int32_t* ef,
                            const uint8_t* fixed) {
+  if (FL == FL_SGRID && USE_REF && g_sgrid_tile && (STRICT || g_metric_corners == 2) &&
+      launch_sgrid_tile_metric(st, m, STAGE, x, s, w, stride, alpha, fixed, R, slot, em, ef))
+    return;
   if (!STRICT && g_metric_corners == 4 && fast_hex<FL, STAGE, USE_REF>() && FL != FL_TET4 && !em && !ef) {
     constexpr int F2 = FL == FL_TET4 ? FL_HEX8 : FL;
     if (s && alpha != 0.0)
@@ -1578,7 +1599,6 @@ static void launch_grad_gather(cudaStream_t st, const MeshDev& m, const double* 
   }
 }
 
-#include "pms_sgrid_tile.cuh"
 #include "pms_elem_ws.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -2188,9 +2208,10 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_metric_multi, launch_refine_sgrid, launch_surf_project, launch_surf_snap, launch_surf_normals};
 
 const Launchers* launchers() { return &g_launchers; }
-void set_variant(int metric_corners, int grad_corners) {
+void set_variant(int metric_corners, int grad_corners, int sgrid_tile) {
   g_metric_corners = metric_corners;
   g_grad_corners = grad_corners;
+  g_sgrid_tile = sgrid_tile;
 }
 
 }  // namespace PMS_NS

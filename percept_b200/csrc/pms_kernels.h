@@ -173,7 +173,7 @@ struct Launchers {
   // alphas[k], out_d[slot + nb + k] = number of invalid elements at alphas[k].  Returns false when not available
   // (tet4, strict build, ShapeB1 without reference mesh).
   bool (*metric_multi)(cudaStream_t, const MeshDev&, int stage, int use_ref, int nb, const double* x, const double* s,
-                       const double* w, long long stride, const double* alphas, const Reduce&, int slot);
+                       const double* w, long long stride, const double* alphas, const Reduce&, int slot, const uint8_t* fixed);
   // StructuredGridRefiner: 2x prolongation of a 3-component nodal field of one block (coarse ni x nj x nk nodes at
   // src + src_off, component stride src_stride) onto the (2ni-1) x (2nj-1) x (2nk-1) block at dst + dst_off
   void (*refine_sgrid)(cudaStream_t, int ni, int nj, int nk, const double* src, long long src_off, long long src_stride,
@@ -192,5 +192,5 @@ struct Launchers {
 
 }  // namespace pmsk
 
-namespace pms_fast { const pmsk::Launchers* launchers(); void set_variant(int metric_corners, int grad_corners); }
-namespace pms_strict { const pmsk::Launchers* launchers(); void set_variant(int metric_corners, int grad_corners); }
+namespace pms_fast { const pmsk::Launchers* launchers(); void set_variant(int metric_corners, int grad_corners, int sgrid_tile = 1); }
+namespace pms_strict { const pmsk::Launchers* launchers(); void set_variant(int metric_corners, int grad_corners, int sgrid_tile = 1); }

@@ -346,6 +346,226 @@ __global__ void __launch_bounds__(WS_NC + WS_NH, 1) k_sgrid_tile_ws(const MeshDe
   grid_reduce<OpSum, 1, true, 1, WS_NC>(val, inv, R, slot);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Metric-only tile kernel (the line search's passes, total_element_metric.cpp:271-307 / Def.hpp:330-388): the same TMA
+// plane staging — x, the reference mesh w, the search direction s and the fixed mask, one bulk copy per node row — and
+// the same compute / producer split, without exchange or node phase.  NB = 1: the metric at x + alpha*s (s may be
+// absent: alpha = 0).  NB = 8 / 12 / 16: the metric at NB trial step lengths from the per-corner polynomial
+// coefficients (hex_metric_multi).  The step is applied to unfixed nodes only (update_coordinates.cpp:255-256).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TM_ROWS = WS_PY;                         // node rows of a tile's patch
+template <int NARR>
+struct TmPlane {
+  static constexpr int DOUBLES = NARR * 3 * TM_ROWS * TL_ROWP + TM_ROWS * 8;  // + 64 mask bytes per row
+};
+#ifndef TM_CORNER_UNROLL
+#define TM_CORNER_UNROLL 8  // (4: 3.87 / 5.21 ms, 1: 3.66 / 4.47 ms, 8: 3.31 / 4.46 ms for 8 / 12 alphas at 256^3)
+#endif
+constexpr int TM_REG_C = 240, TM_REG_H = 24;           // 256 x 240 + 128 x 24 = 64512 = 384 x 168
+template <int NB>
+struct TileAlphas {
+  double a[NB];
+};
+
+// helper thread h issues row h of node plane kp: NARR*3 double rows (arrays a0, a1[, a2]) then the mask rows
+template <int NARR>
+__device__ __forceinline__ void tm_stage_plane(double* buf, unsigned long long* bar, const MeshDev& m, const double* a0,
+                                               const double* a1, const double* a2, const uint8_t* fixed, const long long stride,
+                                               const int i0, const int j0, const int kp, const int h) {
+  const int ac = h / TM_ROWS, row = h % TM_ROWS;  // ac = array * 3 + component; ac == NARR*3: the fixed mask
+  const int rows = min(TM_ROWS, m.nj - j0);
+  if (kp < m.nk && ac <= NARR * 3 && row < rows) {
+    const long long nrow = m.node_off + i0 + (long long)m.ni * ((j0 + row) + (long long)m.nj * kp);
+    if (ac < NARR * 3) {
+      const long long a = nrow & ~1LL;
+      const long long n = stride - a < TL_ROWP ? stride - a : TL_ROWP;
+      const double* src = ac < 3 ? a0 : (ac < 6 ? a1 : a2);
+      const unsigned nb = (unsigned)n * 8u;
+      mbar_arrive_expect_tx(bar, nb);
+      bulk_g2s(buf + (ac * TM_ROWS + row) * TL_ROWP, src + (ac % 3) * stride + a, nb, bar);
+    } else {
+      const long long a = nrow & ~15LL;
+      const long long n = stride - a < 64 ? stride - a : 64;
+      mbar_arrive_expect_tx(bar, (unsigned)n);
+      bulk_g2s(buf + NARR * 3 * TM_ROWS * TL_ROWP + row * 8, fixed + a, (unsigned)n, bar);
+    }
+  } else {
+    mbar_arrive(bar);
+  }
+}
+
+struct TmVerts {  // V(p, r) of one array from two staged planes (p may be a run-time value: selects, no indexed arrays)
+  const double* pl[2];
+  int o[2][2];
+  PMS_DI double operator()(int p, int r) const {
+    const double* b = (p & 4) ? pl[1] : pl[0];
+    const int off = (p & 4) ? ((p & 2) ? o[1][1] : o[1][0]) : ((p & 2) ? o[0][1] : o[0][0]);
+    return b[r * (TM_ROWS * TL_ROWP) + off + (p & 1)];
+  }
+};
+struct TmVertsMasked {  // the search direction: zero at fixed nodes (bit p of fx)
+  TmVerts v;
+  unsigned fx;
+  PMS_DI double operator()(int p, int r) const { return ((fx >> p) & 1u) ? 0.0 : v(p, r); }
+};
+
+template <int STAGE, int NB, bool WITH_S>
+__global__ void __launch_bounds__(WS_NC + WS_NH, 1) k_sgrid_tile_metric(const MeshDev m, const double* __restrict__ x,
+                                                                        const double* __restrict__ s, const double* __restrict__ w,
+                                                                        const long long stride, const uint8_t* __restrict__ fixed,
+                                                                        const TileAlphas<NB> al, const int ntx, const int nty,
+                                                                        const int kc, const Reduce R, const int slot,
+                                                                        double* __restrict__ em, int32_t* __restrict__ ef) {
+  constexpr int NARR = WITH_S ? 3 : 2;  // staged arrays: x, w[, s]
+  constexpr int PLANE = TmPlane<NARR>::DOUBLES;
+  extern __shared__ double sm[];
+  double* const planes = sm;  // [WS_NPL][PLANE]
+  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sm + WS_NPL * PLANE);
+  unsigned long long* const pfull = bars;            // [WS_NPL]
+  unsigned long long* const pempty = bars + WS_NPL;  // [WS_NPL]
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x % (ntx * nty), chunk = blockIdx.x / (ntx * nty);
+  const int i0 = (tile % ntx) * TL_X, j0 = (tile / ntx) * WS_TY;
+  const int nci = m.ni - 1, ncj = m.nj - 1, nck = m.nk - 1;
+  const int actx = min(TL_X, nci - i0), acty = min(WS_TY, ncj - j0);
+  const int kb = chunk * kc, ke = min(kb + kc, nck);
+  const int nlay = ke - kb;
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < WS_NPL; b++) {
+      mbar_init(&pfull[b], WS_NH);
+      mbar_init(&pempty[b], WS_NC);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= WS_NC) {
+    // ------------------------------------------------------------------------------ producer warps
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TM_REG_H));
+    const int h = tid - WS_NC;
+#pragma unroll 1
+    for (int p = 0; p < WS_NPL - 1; p++)
+      tm_stage_plane<NARR>(planes + p * PLANE, &pfull[p], m, x, w, s, fixed, stride, i0, j0, kb + p, h);
+#pragma unroll 1
+    for (int rel = 0; rel < nlay; rel++) {  // plane rel+3 goes where plane rel-1 was
+      const int pr = rel + WS_NPL - 1, u = pr / WS_NPL;
+      if (u >= 1) mbar_wait(&pempty[pr % WS_NPL], (unsigned)((u - 1) & 1));
+      tm_stage_plane<NARR>(planes + (pr % WS_NPL) * PLANE, &pfull[pr % WS_NPL], m, x, w, s, fixed, stride, i0, j0, kb + pr, h);
+    }
+    // no bulk copy may be in flight when the CTA exits
+    for (int pr = nlay + 1; pr < nlay + WS_NPL - 1; pr++) mbar_wait(&pfull[pr % WS_NPL], (unsigned)((pr / WS_NPL) & 1));
+    return;
+  }
+
+  // ---------------------------------------------------------------------------------- compute warps
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TM_REG_C));
+  const int tx = tid & 31, ty = tid >> 5;
+  const bool active = tx < actx && ty < acty;
+  double sums[NB];
+  unsigned cnt[NB];
+#pragma unroll
+  for (int q = 0; q < NB; q++) {
+    sums[q] = 0.0;
+    cnt[q] = 0;
+  }
+  const int par0 = (int)((m.node_off + i0) & 1LL), pni = m.ni & 1, pnj = m.nj & 1;
+  const long long rowbase = m.node_off + i0 + (long long)m.ni * (j0 + ty);  // first node of this thread's lower row, plane 0
+  mbar_wait(&pfull[0], 0);
+#pragma unroll 1
+  for (int rel = 0; rel < nlay; rel++) {
+    const int k = kb + rel;
+    mbar_wait(&pfull[(rel + 1) % WS_NPL], (unsigned)(((rel + 1) / WS_NPL) & 1));
+    if (active) {
+      const double* const p0 = planes + (rel % WS_NPL) * PLANE;
+      const double* const p1 = planes + ((rel + 1) % WS_NPL) * PLANE;
+      TmVerts VC, VO, VS;
+      VC.pl[0] = p0;
+      VC.pl[1] = p1;
+      VO.pl[0] = p0 + 3 * TM_ROWS * TL_ROWP;
+      VO.pl[1] = p1 + 3 * TM_ROWS * TL_ROWP;
+      VS.pl[0] = p0 + 6 * TM_ROWS * TL_ROWP;
+      VS.pl[1] = p1 + 6 * TM_ROWS * TL_ROWP;
+      unsigned fx = 0;
+#pragma unroll
+      for (int dk = 0; dk < 2; dk++)
+#pragma unroll
+        for (int dj = 0; dj < 2; dj++) {
+          const int par = (par0 + pni * ((j0 + ty + dj + pnj * (k + dk)) & 1)) & 1;
+          const int o = (ty + dj) * TL_ROWP + tx + par;
+          VC.o[dk][dj] = o;
+          VO.o[dk][dj] = o;
+          VS.o[dk][dj] = o;
+          if (WITH_S) {  // fixed flags of the row's two nodes: the mask row was staged from the 16-byte boundary below its first node
+            const uint8_t* mrow = reinterpret_cast<const uint8_t*>((dk ? p1 : p0) + NARR * 3 * TM_ROWS * TL_ROWP) + (ty + dj) * 64 +
+                                  (int)((rowbase + (long long)m.ni * dj + (long long)m.ni * m.nj * (k + dk)) & 15LL) + tx;
+            fx |= (mrow[0] ? 1u : 0u) << (dk * 4 + dj * 2);
+            fx |= (mrow[1] ? 1u : 0u) << (dk * 4 + dj * 2 + 1);
+          }
+        }
+      const long long e = m.elem_off + (i0 + tx) + (long long)nci * ((j0 + ty) + (long long)ncj * k);
+      if (NB == 1) {
+        double vc[8][3], vo[8][3];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            double xv = VC(a, r);
+            if (WITH_S) {
+              if (!((fx >> a) & 1u)) {
+                const double dt = al.a[0] * VS(a, r);  // update_coordinates.cpp:255-256
+                xv += dt;
+              }
+            }
+            vc[a][r] = xv;
+            vo[a][r] = VO(a, r);
+          }
+        bool valid;
+        double mm;
+        if (STRICT) {
+          mm = element_metric<FL_SGRID, STAGE, true>(vc, vo, valid);
+        } else if (STAGE == 1) {
+          mm = hex_shapeb1_metric_ilp(vc, vo, valid);
+        } else {
+          double dummy[8][3];
+          mm = hex_metric_fast<STAGE, false>(vc, vo, valid, dummy);
+        }
+        sums[0] += mm;
+        cnt[0] += valid ? 0 : 1;
+        if (em) em[e] = mm;
+        if (ef) ef[e] = valid ? 0 : 1;
+      } else {
+        TmVertsMasked VSM;
+        VSM.v = VS;
+        VSM.fx = fx;
+        double es[NB];
+#pragma unroll
+        for (int q = 0; q < NB; q++) es[q] = 0.0;
+        unsigned invmask;
+        hex_metric_multi<STAGE, NB, TM_CORNER_UNROLL>(VC, VSM, VO, al.a, es, invmask);
+#pragma unroll
+        for (int q = 0; q < NB; q++) {
+          sums[q] += es[q];
+          cnt[q] += (invmask >> q) & 1u;
+        }
+      }
+    }
+    mbar_arrive(&pempty[rel % WS_NPL]);
+  }
+  if (NB == 1) {
+    double v[1] = {sums[0]};
+    grid_reduce<OpSum, 1, true, 1, WS_NC>(v, (unsigned long long)cnt[0], R, slot);
+  } else {
+    double v[2 * NB];
+#pragma unroll
+    for (int q = 0; q < NB; q++) {
+      v[q] = sums[q];
+      v[NB + q] = (double)cnt[q];
+    }
+    grid_reduce<OpSum, 2 * NB, false, 1, WS_NC>(v, 0ull, R, slot);
+  }
+}
+
 // seam nodes: the 8 adjacent cells' contributions in (dk,dj,di) order, as k_grad_gather_sgrid adds them
 template <int TJ>
 __global__ void __launch_bounds__(NT) k_sgrid_seam_sum(const MeshDev m, const SeamDev seam, const uint8_t* __restrict__ fixed,
@@ -394,16 +614,6 @@ __global__ void __launch_bounds__(NT) k_sgrid_seam_sum(const MeshDev m, const Se
   g[n] = a0;
   g[stride + n] = a1;
   g[2 * stride + n] = a2;
-}
-
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
-  }
-  return n;
 }
 
 // k-chunk length that minimises (rounds of CTAs over the SMs) x (layers per CTA incl. the warm-up layer)
@@ -462,4 +672,62 @@ static bool launch_grad_fused_sgrid(cudaStream_t st, const MeshDev& m, int stage
   if (nJ + nI > 0)
     k_sgrid_seam_sum<WS_TY><<<(unsigned)((nJ + nI + NT - 1) / NT), NT, 0, st>>>(m, sd, fixed, g, stride, nJ, nI);
   return true;
+}
+
+template <int STAGE, int NB, bool WITH_S>
+static bool launch_sgrid_tile_metric3(cudaStream_t st, const MeshDev& m, const double* x, const double* s, const double* w,
+                                      long long stride, const uint8_t* fixed, const double* alphas, const Reduce& R, int slot,
+                                      double* em, int32_t* ef) {
+  const int nci = m.ni - 1, ncj = m.nj - 1, nck = m.nk - 1;
+  const int ntx = (nci + TL_X - 1) / TL_X, nty = (ncj + WS_TY - 1) / WS_TY;
+  const long long ntiles = (long long)ntx * nty;
+  // chunks of k: no warm-up layer here, but the same balance rule
+  const int kc = tl_pick_chunk(ntiles, nck);
+  const long long grid = ntiles * ((nck + kc - 1) / kc);
+  if (grid > R.max_blocks || grid > 0x7fffffffLL) return false;
+  constexpr size_t smem = (size_t)(WS_NPL * TmPlane<WITH_S ? 3 : 2>::DOUBLES) * sizeof(double) + 2 * WS_NPL * 8;
+  auto kern = k_sgrid_tile_metric<STAGE, NB, WITH_S>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  TileAlphas<NB> al;
+  for (int q = 0; q < NB; q++) al.a[q] = alphas[q];
+  kern<<<(unsigned)grid, WS_NC + WS_NH, smem, st>>>(m, x, s, w, stride, fixed, al, ntx, nty, kc, R, slot, em, ef);
+  return true;
+}
+
+static bool sgrid_tile_ok(const MeshDev& m, const double* x, const double* s, const double* w, long long stride, const uint8_t* fixed) {
+  return !(m.kind != KIND_SGRID || m.ni < 2 || m.nj < 2 || m.nk < 2 || ((uintptr_t)x & 15) || ((uintptr_t)w & 15) ||
+           ((uintptr_t)s & 15) || ((uintptr_t)fixed & 15) || (stride & 15) || !fixed);
+}
+
+// metric at x + alpha*s (s null or alpha 0: at x); returns false if this block cannot take the tile path
+static bool launch_sgrid_tile_metric(cudaStream_t st, const MeshDev& m, int stage, const double* x, const double* s, const double* w,
+                                     long long stride, double alpha, const uint8_t* fixed, const Reduce& R, int slot, double* em,
+                                     int32_t* ef) {
+  if (!sgrid_tile_ok(m, x, s, w, stride, fixed)) return false;
+  const bool with_s = s && alpha != 0.0;
+  if (stage == 0)
+    return with_s ? launch_sgrid_tile_metric3<0, 1, true>(st, m, x, s, w, stride, fixed, &alpha, R, slot, em, ef)
+                  : launch_sgrid_tile_metric3<0, 1, false>(st, m, x, nullptr, w, stride, fixed, &alpha, R, slot, em, ef);
+  return with_s ? launch_sgrid_tile_metric3<1, 1, true>(st, m, x, s, w, stride, fixed, &alpha, R, slot, em, ef)
+                : launch_sgrid_tile_metric3<1, 1, false>(st, m, x, nullptr, w, stride, fixed, &alpha, R, slot, em, ef);
+}
+
+template <int NB>
+static bool launch_sgrid_tile_multi1(cudaStream_t st, const MeshDev& m, int stage, const double* x, const double* s, const double* w,
+                                     long long stride, const uint8_t* fixed, const double* alphas, const Reduce& R, int slot) {
+  if (stage == 0) return launch_sgrid_tile_metric3<0, NB, true>(st, m, x, s, w, stride, fixed, alphas, R, slot, nullptr, nullptr);
+  return launch_sgrid_tile_metric3<1, NB, true>(st, m, x, s, w, stride, fixed, alphas, R, slot, nullptr, nullptr);
+}
+static bool launch_sgrid_tile_multi(cudaStream_t st, const MeshDev& m, int stage, int nb, const double* x, const double* s,
+                                    const double* w, long long stride, const uint8_t* fixed, const double* alphas, const Reduce& R,
+                                    int slot) {
+  if (STRICT || !s || !sgrid_tile_ok(m, x, s, w, stride, fixed)) return false;
+  if (nb == 8) return launch_sgrid_tile_multi1<8>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
+  if (nb == 12) return launch_sgrid_tile_multi1<12>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
+  if (nb == 16) return launch_sgrid_tile_multi1<16>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
+  return false;
 }
