@@ -20,6 +20,8 @@
 #include <numeric>
 #include <thread>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "pms_ctx.h"
 
 using pmsk::MeshDev;
@@ -40,11 +42,23 @@ void pms_ctx::bump(const char* name) { field(name).version++; }
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+// NVTX ranges (header-only NVTX3; no cost without a tool attached) named like the reference's stk TimeBlocks, so that a
+// timeline of this library reads like the reference's printTimersTableStructured(): "GATM pr 1"
+// (GenericAlgorithm_total_element_metric.cpp:190-211), "GA_gg_1 calc grad pf 1" (gradient_functors.hpp:427-448),
+// "GATM1 parallel_for" (GenericAlgorithm_update_coordinates.cpp:306), "RMSCGI::run_one_iteration()" (Def.hpp:1014-1016)
+const char* const FAM_NVTX[FAM_COUNT] = {"GATM pr 1",   "GA_gg_1 calc grad pf 1", "nodal_field BLAS-1",       "GATM1 parallel_for",
+                                         "get_alpha_0", "get_edge_lengths",       "comm_fields / sum_fields", "StructuredGridRefiner"};
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct Timed {
   pms_ctx* c;
   int fam;
   cudaEvent_t a = nullptr, b = nullptr;
-  Timed(pms_ctx* cc, int f, int nlaunch = 1) : c(cc), fam(f) {
+  NvtxRange range;
+  Timed(pms_ctx* cc, int f, int nlaunch = 1) : c(cc), fam(f), range(FAM_NVTX[f]) {
     c->launches += nlaunch;
     c->fam_launches[fam] += nlaunch;
     if (c->timing) {
@@ -1112,6 +1126,7 @@ struct Driver {
 
   // run_one_iteration, Def.hpp:1010-1093
   double run_one_iteration() {
+    NvtxRange range("RMSCGI::run_one_iteration()");
     bool total_valid = false;
     if (st->iter == 0) {
       op_edge_lengths(c);
