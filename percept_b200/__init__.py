@@ -10,7 +10,8 @@ import os as _os
 from .capi import AOS, SOA, TET4, HEX8, Api, Ctx, SmootherError, State  # noqa: F401
 
 _HERE = _os.path.dirname(_os.path.abspath(__file__))
-LIB_PATH = _os.path.join(_HERE, "lib", "libpms.so")
+# PMS_LIB: an A/B build of the same library (tools/build_variant.sh); default the in-tree build
+LIB_PATH = _os.environ.get("PMS_LIB") or _os.path.join(_HERE, "lib", "libpms.so")
 
 
 def _load():

@@ -21,6 +21,18 @@
 #ifndef PMS_GRAD_VIA_GRAM
 #define PMS_GRAD_VIA_GRAM 1
 #endif
+#ifndef PMS_GRAD_EDGE_ACC
+#define PMS_GRAD_EDGE_ACC 1  // gradient accumulated per hex EDGE first (see hex_metric_fast_v)
+#endif
+#ifndef PMS_RSQRT_CUBIC
+#define PMS_RSQRT_CUBIC 1
+#endif
+#ifndef PMS_NO_OK_SELECT
+#define PMS_NO_OK_SELECT 1  // ShapeB1 gradient: no per-corner selects on detA > 0 (the element-level rule covers them)
+#endif
+#ifndef PMS_USE_BRANCH
+#define PMS_USE_BRANCH 0    // invalid element: branch around the 24 stores instead of 24 selects
+#endif
 
 
 namespace pmsdev {
@@ -28,6 +40,13 @@ namespace pmsdev {
 PMS_DI double fast_rsqrt(double x) {
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#if PMS_RSQRT_CUBIC
+  // one third-order step: with e = (1 - x r^2)/2 the exact value is r (1 - 2e)^(-1/2) = r (1 + e + 1.5 e^2 + O(e^3)); the
+  // seed carries >= 20 bits, so the remainder 2.5 e^3 is below 2^-58.  5 FP64 on a 4-deep chain instead of 6 on a 6-deep one.
+  const double h = (0.5 * x) * r;
+  const double e = fma(-h, r, 0.5);
+  return fma(r * e, fma(1.5, e, 1.0), r);
+#else
   const double hx = 0.5 * x;
 #pragma unroll
   for (int it = 0; it < 2; it++) {
@@ -36,6 +55,7 @@ PMS_DI double fast_rsqrt(double x) {
     r = fma(r, e, r);
   }
   return r;
+#endif
 }
 PMS_DI double fast_rcp(double x) {
   double r;
@@ -100,11 +120,19 @@ PMS_DI void corner_edge(const V& v, int c, double (&e)[3]) {
 // reference mesh.  grad[a][r] accumulates d(metric)/d(x_a,r); the caller applies the element-level validity rule.
 // Written branch-free (selects instead of `if (detA > 0)`): the 8 corners then sit in ONE basic block and ptxas can
 // interleave their dependent FP64 chains, which is what hides the ~9-cycle DFMA latency at 2 warps per scheduler.
+//
+// Gradient assembly (PMS_GRAD_EDGE_ACC): a corner's derivative dM[r][s] w.r.t. its canonical edge along axis s goes
+// +dM to the edge's high vertex and -dM to its low vertex, and each of the 12 hex edges is the canonical edge of exactly
+// its two end corners.  So the two corners' terms  k1 (A G)[r][s] - k2 cof(A)[r][s]  are chained by FMA into one edge
+// accumulator E (1 DMUL + 3 DFMA per component), and a vertex's gradient is the signed sum of its three edges' E
+// (2 DADD per component): 12*12 + 8*6 = 192 FP64 per hex instead of 8*(18 + 18) = 288 for "form dM, then add it to
+// both ends".  Same terms, different association: differs from the other form by rounding only.
 template <int STAGE, bool GRAD, class VC, class VO>
 PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double (&grad)[8][3]) {
   valid = true;
   double val0 = 0.0, val1 = 0.0;
-  if (GRAD) {
+  double E[3][4][3];  // [axis s][edge index among the 4 along s][component r]
+  if (GRAD && !PMS_GRAD_EDGE_ACC) {
 #pragma unroll
     for (int a = 0; a < 8; a++)
 #pragma unroll
@@ -119,12 +147,13 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
     corner_edge<0>(vo, c, w0);
     corner_edge<1>(vo, c, w1);
     corner_edge<2>(vo, c, w2);
-    double K0[3], K1[3], K2[3];
-    cross3(a1, a2, K0);
-    const double detA = dot3(a0, K0);
+    double K[3][3];  // K[s] = cofactor column s of A = [a0 a1 a2]
+    cross3(a1, a2, K[0]);
+    const double detA = dot3(a0, K[0]);
     const bool ok = detA > 0.0;
     if (!ok) valid = false;
-    double dM[3][3];  // dM[r][s]: derivative w.r.t. component r of the edge along axis s
+    // d(term)/d(edge s, component r) = k1 * Tp[r][s] + nk2 * K[s][r]
+    double Tp[3][3], k1 = 0.0, nk2 = 0.0;
     if (STAGE == 0) {
       double C0[3];
       cross3(w1, w2, C0);
@@ -133,15 +162,9 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
       const double vp = vv > 0.0 ? vv : 0.0;  // contributes 0 (value and gradient) when vv <= 0
       ((c & 1) ? val1 : val0) += vp * vp;
       if (GRAD) {
-        cross3(a2, a0, K1);
-        cross3(a0, a1, K2);
-        const double s = -2.0 * vp;
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-          dM[r][0] = s * K0[r];
-          dM[r][1] = s * K1[r];
-          dM[r][2] = s * K2[r];
-        }
+        cross3(a2, a0, K[1]);
+        cross3(a0, a1, K[2]);
+        nk2 = -2.0 * vp;
       }
     } else {
       double C0[3], C1[3], C2[3];
@@ -149,7 +172,7 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
       cross3(w2, w0, C1);
       cross3(w0, w1, C2);
       const double detW = dot3(w0, C0);
-      double Tp[3][3], ys[3];
+      double ys[3];
       if (GRAD && PMS_GRAD_VIA_GRAM) {
         // (T'C)[r][j] = sum_i a_i[r] (C_i.C_j): with the Gram matrix G = C C^T of the reference cofactors (6 dot
         // products) B = A G serves both y = |T'|^2 = A:B and the derivative, and T' itself is never formed:
@@ -177,8 +200,11 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
       if (GRAD && PMS_GRAD_VIA_GRAM) {
         // one rsqrt serves both: u = rsqrt(y (P detA)^2) = 1/(sqrt(y) P detA), y u = sqrt(y)/(P detA), times detA = sqrt(y)/P
         // (saves the separate reciprocal of detA: 7 FP64 per corner)
+        // No select on the argument: a corner with detA <= 0 makes the element invalid, the ShapeB1 gradient of an
+        // invalid element is discarded as a whole (gradient_functors.hpp:391) and the value below is selected by `ok`,
+        // so whatever inf/NaN the rsqrt of a zero argument produces never reaches a result.
         const double Pd = P * detA;
-        yrd = y * fast_rsqrt(ok ? y * Pd * Pd : 1.0);
+        yrd = y * fast_rsqrt((PMS_NO_OK_SELECT || ok) ? y * Pd * Pd : 1.0);
         yr = yrd * detA;
       } else {
         yr = y * fast_rsqrt(ok ? y * P * P : 1.0);
@@ -186,22 +212,27 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
       const double q = y * yr;   // y^1.5/P
       ((c & 1) ? val1 : val0) += ok ? q - detW : 0.0;
       if (GRAD) {
-        cross3(a2, a0, K1);
-        cross3(a0, a1, K2);
-        const double k1 = ok ? 3.0 * yr : 0.0;
-        // detA <= 0: corner contributes nothing (SmootherMetric.hpp:835)
-        const double nk2 = ok ? (PMS_GRAD_VIA_GRAM ? -y * yrd : -q * fast_rcp(detA)) : 0.0;
+        cross3(a2, a0, K[1]);
+        cross3(a0, a1, K[2]);
+        // detA <= 0: the corner contributes nothing (SmootherMetric.hpp:835) - with the Gram form that is implied by
+        // the element-level rule above (the caller drops the whole gradient when !valid), so no per-corner selects
+        if (PMS_GRAD_VIA_GRAM && PMS_NO_OK_SELECT) {
+          k1 = 3.0 * yr;
+          nk2 = -y * yrd;
+        } else if (PMS_GRAD_VIA_GRAM) {
+          k1 = ok ? 3.0 * yr : 0.0;
+          nk2 = ok ? -y * yrd : 0.0;
+        } else {
+          k1 = ok ? 3.0 * yr : 0.0;
+          nk2 = ok ? -q * fast_rcp(detA) : 0.0;
+        }
+        if (!PMS_GRAD_VIA_GRAM) {  // Tp held T' = A C^T: the derivative needs T' C
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-          const double (&t)[3] = Tp[r];
-          if (PMS_GRAD_VIA_GRAM) {
-            dM[r][0] = k1 * t[0] + nk2 * K0[r];
-            dM[r][1] = k1 * t[1] + nk2 * K1[r];
-            dM[r][2] = k1 * t[2] + nk2 * K2[r];
-          } else {
-            dM[r][0] = k1 * (t[0] * C0[0] + t[1] * C0[1] + t[2] * C0[2]) + nk2 * K0[r];
-            dM[r][1] = k1 * (t[0] * C1[0] + t[1] * C1[1] + t[2] * C1[2]) + nk2 * K1[r];
-            dM[r][2] = k1 * (t[0] * C2[0] + t[1] * C2[1] + t[2] * C2[2]) + nk2 * K2[r];
+          for (int r = 0; r < 3; r++) {
+            const double t0 = Tp[r][0], t1 = Tp[r][1], t2 = Tp[r][2];
+            Tp[r][0] = t0 * C0[0] + t1 * C0[1] + t2 * C0[2];
+            Tp[r][1] = t0 * C1[0] + t1 * C1[1] + t2 * C1[2];
+            Tp[r][2] = t0 * C2[0] + t1 * C2[1] + t2 * C2[2];
           }
         }
       }
@@ -210,13 +241,34 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
 #pragma unroll
       for (int s = 0; s < 3; s++) {
         const int lo = c & ~(1 << s), hi = lo | (1 << s);
+        if (PMS_GRAD_EDGE_ACC) {
+          const int ei = ((lo >> (s + 1)) << s) | (lo & ((1 << s) - 1));  // lo with bit s squeezed out
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-          grad[hi][r] += dM[r][s];
-          grad[lo][r] -= dM[r][s];
+          for (int r = 0; r < 3; r++) {
+            if (STAGE == 0)
+              E[s][ei][r] = (c == lo) ? nk2 * K[s][r] : fma(nk2, K[s][r], E[s][ei][r]);
+            else
+              E[s][ei][r] = fma(nk2, K[s][r], (c == lo) ? k1 * Tp[r][s] : fma(k1, Tp[r][s], E[s][ei][r]));
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            const double d = STAGE == 0 ? nk2 * K[s][r] : k1 * Tp[r][s] + nk2 * K[s][r];
+            grad[hi][r] += d;
+            grad[lo][r] -= d;
+          }
         }
       }
     }
+  }
+  if (GRAD && PMS_GRAD_EDGE_ACC) {
+#pragma unroll
+    for (int v = 0; v < 8; v++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const double e0 = E[0][v >> 1][r], e1 = E[1][((v >> 2) << 1) | (v & 1)][r], e2 = E[2][v & 3][r];
+        grad[v][r] = (((v & 1) ? e0 : -e0) + ((v & 2) ? e1 : -e1)) + ((v & 4) ? e2 : -e2);
+      }
   }
   return val0 + val1;
 }

@@ -700,10 +700,17 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
     const long long ge = m.elem_off + e_cur;
     if (GRAD) {
       const bool use = valid || STAGE == 0;  // gradient_functors.hpp:391, Def.hpp:1219
+      if (use || !PMS_USE_BRANCH) {  // a branch, not 24 selects: invalid elements are rare where they matter (ShapeB1 stage)
 #pragma unroll
-      for (int a = 0; a < NN; a++)
+        for (int a = 0; a < NN; a++)
 #pragma unroll
-        for (int r = 0; r < 3; r++) eg[(long long)(a * 3 + r) * eg_stride + ge] = use ? grad[vpos<FL, FAST>(a)][r] : 0.0;
+          for (int r = 0; r < 3; r++) eg[(long long)(a * 3 + r) * eg_stride + ge] = (PMS_USE_BRANCH || use) ? grad[vpos<FL, FAST>(a)][r] : 0.0;
+      } else {
+#pragma unroll
+        for (int a = 0; a < NN; a++)
+#pragma unroll
+          for (int r = 0; r < 3; r++) eg[(long long)(a * 3 + r) * eg_stride + ge] = 0.0;
+      }
     }
     const bool counted = FL == FL_SGRID || own_cur != 0;
     if (counted) {

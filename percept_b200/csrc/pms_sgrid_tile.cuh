@@ -326,10 +326,17 @@ __global__ void __launch_bounds__(WS_NC + WS_NH, 1) k_sgrid_tile_ws(const MeshDe
       }
       const bool use = valid || STAGE == 0;  // gradient_functors.hpp:391
       double* const exc = ex + (rel & 1) * WS_EX + (ty + 1) * WS_EXP + (tx + 1);
+      if (use || !PMS_USE_BRANCH) {
 #pragma unroll
-      for (int a = 0; a < 8; a++)
+        for (int a = 0; a < 8; a++)
 #pragma unroll
-        for (int r = 0; r < 3; r++) exc[(a * 3 + r) * WS_EXPL] = use ? grad[a][r] : 0.0;
+          for (int r = 0; r < 3; r++) exc[(a * 3 + r) * WS_EXPL] = (PMS_USE_BRANCH || use) ? grad[a][r] : 0.0;
+      } else {
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+          for (int r = 0; r < 3; r++) exc[(a * 3 + r) * WS_EXPL] = 0.0;
+      }
       if (k >= kb) {
         val[0] += mm;
         inv += valid ? 0 : 1;
