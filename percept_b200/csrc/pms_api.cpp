@@ -592,82 +592,91 @@ void build_bricks(pms_ctx* c) {
   c->bricks_wv = W.version;
 }
 
-// Plan of the one-kernel unstructured gradient: slab length from the largest element-index span around a node, nodes
-// grouped by the slab of their last adjacent element (ascending node id inside a group), ring + counters.
+// Plan of the one-kernel unstructured hex8 gradient (pms_elem_ws.cuh): nodes listed by the iteration in which their last
+// adjacent element is evaluated (tile = 128 consecutive elements, iteration = tile / grid), cut into batches of grid*128,
+// the per-node CSR walk resolved into scratch offsets, the slabs each batch has to wait for, and the delay D.
 void build_ws_plan(pms_ctx* c) {
   c->ws_failed = true;
-  int nsm = 0;
-  if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess || nsm < 1) return;
-  int coop = 0;
-  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
-  if (!coop) return;
-  const long long E = c->E, N = c->N, nwarps = (long long)nsm * 8;
-  const int npe = c->topo == 4 ? 4 : 8;
-  long long span = 0;
+  const int G = c->L->grad_ws_grid();
+  if (G < 1 || c->topo != 8) return;
+  const long long E = c->E, N = c->N, Epad = c->Epad;
+  constexpr int K = 4, TILE = 128;  // EG_K, NTP of the kernel TU
+  // iterations a CTA may run ahead of the slowest one before it has to wait for it (costs as many drain iterations at the end)
+  constexpr int LAG = 8;
+  if (24 * Epad >= (1ll << 31) || N >= (1ll << 31)) return;  // 32-bit scratch offsets / node ids
+  const long long per = (long long)G * TILE;
+  const long long ntiles = (E + TILE - 1) / TILE, niter_e = (ntiles + G - 1) / G;
+  if (niter_e < 2) return;  // a single iteration: nothing to ride on
+  // completion iteration per node; nodes with more than 8 elements go to the overflow list
+  std::vector<int32_t> comp(N), ovf;
+  std::vector<long long> goff(niter_e + 1, 0);
   for (long long n = 0; n < N; n++) {
     const int64_t p0 = c->h_csr_ptr[n], p1 = c->h_csr_ptr[n + 1];
-    if (p1 > p0) span = std::max<long long>(span, (c->h_csr_ent[p1 - 1] >> 3) - (c->h_csr_ent[p0] >> 3));
+    if (p1 - p0 > 8) {
+      comp[n] = -1;
+      ovf.push_back((int32_t)n);
+      continue;
+    }
+    comp[n] = p1 > p0 ? (int32_t)(((c->h_csr_ent[p1 - 1] >> 3) / TILE) / G) : 0;
+    goff[comp[n] + 1]++;
   }
-  const long long tpw = std::max<long long>(1, (span + 1 + 32 * nwarps - 1) / (32 * nwarps));
-  const long long slab = 32 * nwarps * tpw;
-  if (4 * slab >= E || tpw > (1 << 20)) return;  // the ring would be as large as the full scratch: keep the two-pass path
-  if (!c->d_csr_ent32 || 24 * 4 * slab >= (1ll << 31) || E * 8 >= (1ll << 31)) return;  // the gather's 32-bit index arithmetic
-  const long long ntiles = (E + 31) / 32, tps = nwarps * tpw;
-  const long long nslabs = (ntiles + tps - 1) / tps;
-  if (nslabs >= (1ll << 30)) return;
-  std::vector<long long> goff(nslabs + 1, 0);
-  std::vector<int32_t> grp(N);
-  for (long long n = 0; n < N; n++) {
-    const int64_t p0 = c->h_csr_ptr[n], p1 = c->h_csr_ptr[n + 1];
-    grp[n] = p1 > p0 ? (int32_t)((c->h_csr_ent[p1 - 1] >> 3) / slab) : 0;
-    goff[grp[n] + 1]++;
-  }
-  for (long long s = 0; s < nslabs; s++) goff[s + 1] += goff[s];
-  std::vector<int32_t> gnodes(N);
+  for (long long i = 0; i < niter_e; i++) goff[i + 1] += goff[i];
+  const long long NL = goff[niter_e];
+  const long long nb = (NL + per - 1) / per;
+  if (nb < 1 || nb >= (1ll << 30)) return;
+  std::vector<int32_t> lnode((size_t)nb * per, -1);
   {
     std::vector<long long> fill(goff.begin(), goff.end() - 1);
-    for (long long n = 0; n < N; n++) gnodes[fill[grp[n]]++] = (int32_t)n;
+    for (long long n = 0; n < N; n++)
+      if (comp[n] >= 0) lnode[fill[comp[n]]++] = (int32_t)n;
   }
-  // gather table: the node's CSR walk resolved into ring offsets (an element of slab s sits in ring slot s % 4)
-  long long maxval = 0;
-  for (long long n = 0; n < N; n++) maxval = std::max<long long>(maxval, c->h_csr_ptr[n + 1] - c->h_csr_ptr[n]);
-  const long long tabw = std::max<long long>(4, (maxval + 3) / 4 * 4);
-  if (tabw > 64) return;  // (a node shared by more than 64 elements: keep the two-pass path)
-  const long long ring_elems = 4 * slab;
-  std::vector<int32_t> gtab((size_t)tabw * N, -1);
+  std::vector<int32_t> need(nb);
+  long long D = 2;
+  for (long long j = 0; j < nb; j++) {
+    const long long last = std::min((j + 1) * per, NL) - 1;
+    need[j] = comp[lnode[last]] / K + 1;  // (the list is sorted by completion iteration)
+    D = std::max(D, (long long)need[j] * K - j + 2 + LAG);
+  }
+  // a mesh numbered so wildly that most nodes complete only at the end gains nothing: keep the two-pass path
+  if (nb + D > niter_e + niter_e / 4 + 32) return;
+  std::vector<int32_t> tabA((size_t)nb * per * 4, -1), tabB((size_t)nb * per * 4, -1);
   const unsigned nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  auto parallel_for = [&](long long n, const std::function<void(long long, long long)>& fn) {
+  {
     std::vector<std::thread> th;
-    const long long chunk = (n + nthreads - 1) / nthreads;
+    const long long chunk = (NL + nthreads - 1) / nthreads;
     for (unsigned t = 0; t < nthreads; t++) {
-      const long long a = t * chunk, b = std::min(n, a + chunk);
-      if (a < b) th.emplace_back(fn, a, b);
+      const long long qa = t * chunk, qb = std::min(NL, qa + chunk);
+      if (qa >= qb) break;
+      th.emplace_back([&, qa, qb]() {
+        for (long long q = qa; q < qb; q++) {
+          const long long n = lnode[q];
+          const int64_t p0 = c->h_csr_ptr[n], p1 = c->h_csr_ptr[n + 1];
+          for (int64_t p = p0; p < p1; p++) {
+            const int64_t ent = c->h_csr_ent[p];
+            const int32_t off = (int32_t)((ent & 7) * 3 * Epad + (ent >> 3));
+            const int k = (int)(p - p0);
+            (k < 4 ? tabA : tabB)[(size_t)q * 4 + (k & 3)] = off;
+          }
+        }
+      });
     }
     for (auto& x : th) x.join();
-  };
-  parallel_for(N, [&](long long qa, long long qb) {
-    for (long long q = qa; q < qb; q++) {
-      const long long n = gnodes[q];
-      const int64_t p0 = c->h_csr_ptr[n], p1 = c->h_csr_ptr[n + 1];
-      for (int64_t p = p0; p < p1; p++) {
-        const int64_t ent = c->h_csr_ent[p];
-        const long long e = ent >> 3, s = e / slab;
-        gtab[(size_t)(p - p0) * N + q] = (int32_t)((ent & 7) * 3 * ring_elems + (s % 4) * slab + (e - s * slab));
-      }
-    }
-  });
+  }
   pmsk::WsPlanDev& P = c->ws;
-  P.gtab = dupload(gtab);
-  P.tab_w = (int)tabw;
-  P.tab_n = N;
-  P.slab_elems = slab;
-  P.tiles_per_warp = (int)tpw;
-  P.nslabs = (int)nslabs;
-  P.gnodes = dupload(gnodes);
-  P.goff = dupload(goff);
-  P.ring = dalloc<double>((size_t)3 * npe * 4 * slab);
-  P.counters = dalloc<int>((size_t)2 * nsm);
-  c->ws_grid = nsm;
+  P.grid = G;
+  P.D = (int)D;
+  P.nbatches = (int)nb;
+  P.nslabs = (int)((niter_e + K - 1) / K);
+  P.sleep_ns = 1000;
+  P.niter = std::max(niter_e, nb + D);
+  P.lnode = dupload(lnode);
+  P.tabA = reinterpret_cast<const int4*>(dupload(tabA));
+  P.tabB = reinterpret_cast<const int4*>(dupload(tabB));
+  P.need = dupload(need);
+  P.prog = dalloc<int>((size_t)P.nslabs + 1);
+  P.novf = (long long)ovf.size();
+  P.ovf_nodes = ovf.empty() ? nullptr : dupload(ovf);
+  c->ws_grid = G;
   c->ws_built = true;
   c->ws_failed = false;
 }
@@ -707,19 +716,21 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write
       }
     }
   }
-  if (!fused_ok && !c->structured && c->elem_ws && c->var_grad == 2 && !c->strict_fp && !c->keep_elem) {
+  if (!fused_ok && !c->structured && c->topo == 8 && c->elem_ws && c->var_grad == 2 && !c->strict_fp && !c->keep_elem &&
+      (stage == 0 || use_ref)) {
     if (!c->ws_built && !c->ws_failed) build_ws_plan(c);
     if (c->ws_built) {
-      Timed t(c, FAM_GRADIENT, 1);
-      PMS_CUDA(cudaMemsetAsync(c->ws.counters, 0, (size_t)2 * c->ws_grid * sizeof(int), c->stream));
-      fused_ok = c->L->grad_ws(c->stream, c->dev_blocks[0], c->ws, c->ws_grid, stage, use_ref, X.d, W.d, c->Npad, c->d_fixed,
-                               c->d_node_owned, G.d, write_r ? Rr.d : nullptr, c->R, 0);
+      ensure_eg(c);
+      Timed t(c, FAM_GRADIENT, c->ws.novf > 0 ? 2 : 1);
+      PMS_CUDA(cudaMemsetAsync(c->ws.prog, 0, ((size_t)c->ws.nslabs + 1) * sizeof(int), c->stream));
+      fused_ok = c->L->grad_ws(c->stream, c->dev_blocks[0], c->ws, stage, use_ref, X.d, W.d, c->Npad, c->d_fixed, c->d_node_owned,
+                               G.d, write_r ? Rr.d : nullptr, c->d_eg, c->Epad, c->R, 0);
       if (!fused_ok) {
         cudaGetLastError();
         c->ws_built = false;
         c->ws_failed = true;  // (launch refused: not tried again)
-        c->launches--;
-        c->fam_launches[FAM_GRADIENT]--;
+        c->launches -= c->ws.novf > 0 ? 2 : 1;
+        c->fam_launches[FAM_GRADIENT] -= c->ws.novf > 0 ? 2 : 1;
       } else {
         check_launch(c, "grad_ws");
       }
@@ -1361,7 +1372,7 @@ void pms_destroy(pms_ctx* c) {
                     c->d_csr_ptr,   c->d_csr_ent,   c->d_grp_ptr,    c->d_grp_nodes,  c->d_eg,       c->d_elem_metric,
                     c->d_elem_flag, c->R.partial_d, c->R.partial_u,  c->R.ticket,     c->R.out_d,    c->R.out_u,
                     c->d_send_nodes, c->d_recv_nodes, c->d_send_buf, c->d_recv_buf,   c->d_coll, c->d_skip, c->d_csr_ent32, c->d_if_nodes, c->d_sh_nodes, c->d_sh_cnt, c->d_sh_ptr, c->d_sh_pos,
-                    c->d_if_send, c->d_if_recv, c->d_seam, (void*)c->ws.gnodes, (void*)c->ws.goff, (void*)c->ws.gtab, c->ws.ring, c->ws.counters};
+                    c->d_if_send, c->d_if_recv, c->d_seam, (void*)c->ws.lnode, (void*)c->ws.tabA, (void*)c->ws.tabB, (void*)c->ws.need, c->ws.prog, (void*)c->ws.ovf_nodes};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->h_out_d) cudaFreeHost(c->h_out_d);

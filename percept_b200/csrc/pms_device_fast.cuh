@@ -127,8 +127,13 @@ PMS_DI void corner_edge(const V& v, int c, double (&e)[3]) {
 // accumulator E (1 DMUL + 3 DFMA per component), and a vertex's gradient is the signed sum of its three edges' E
 // (2 DADD per component): 12*12 + 8*6 = 192 FP64 per hex instead of 8*(18 + 18) = 288 for "form dM, then add it to
 // both ends".  Same terms, different association: differs from the other form by rounding only.
-template <int STAGE, bool GRAD, class VC, class VO>
-PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double (&grad)[8][3]) {
+struct NoMid {
+  PMS_DI void operator()() const {}
+};
+// `mid` is invoked once between corners 3 and 4: the one-kernel gradient (pms_elem_ws.cuh) places the second half of its
+// node gather there, half an iteration after the first.
+template <int STAGE, bool GRAD, class VC, class VO, class MID = NoMid>
+PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double (&grad)[8][3], MID mid = MID()) {
   valid = true;
   double val0 = 0.0, val1 = 0.0;
   double E[3][4][3];  // [axis s][edge index among the 4 along s][component r]
@@ -140,6 +145,7 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
   }
 #pragma unroll
   for (int c = 0; c < 8; c++) {
+    if (c == 4) mid();
     double a0[3], a1[3], a2[3], w0[3], w1[3], w2[3];
     corner_edge<0>(vc, c, a0);
     corner_edge<1>(vc, c, a1);

@@ -1188,6 +1188,9 @@ int g_sgrid_tile = 1;  // structured blocks: 1 = TMA-staged tile kernels for the
 #ifndef MULTI_MINB
 #define MULTI_MINB 2
 #endif
+#ifndef MULTI_CORNER_UNROLL_BIG
+#define MULTI_CORNER_UNROLL_BIG 8  // corner-loop unroll of the 12- and 16-alpha kernels (fewer: no spills, run-time vertex addressing)
+#endif
 template <int NB>
 struct AlphaPack {
   double a[NB];
@@ -1243,7 +1246,7 @@ __global__ void __launch_bounds__(NTP, MULTI_MINB) k_metric_multi(const MeshDev 
 #pragma unroll
     for (int k = 0; k < NB; k++) es[k] = 0.0;
     unsigned invmask;
-    hex_metric_multi<STAGE, NB>(VC, VS, VO, al.a, es, invmask);
+    hex_metric_multi<STAGE, NB, (NB >= 12 ? MULTI_CORNER_UNROLL_BIG : 8)>(VC, VS, VO, al.a, es, invmask);
     if (counted) {
 #pragma unroll
       for (int k = 0; k < NB; k++) {
@@ -2211,7 +2214,7 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_group_sum, launch_axpby,         launch_axpbypgz,    launch_set,
                                       launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_cg_s_update_dots, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,
-                                      launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_elem_ws, launch_shared_sum,
+                                      launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_elem_ws, elem_gather_grid, launch_shared_sum,
                                       launch_metric_multi, launch_refine_sgrid, launch_surf_project, launch_surf_snap, launch_surf_normals};
 
 const Launchers* launchers() { return &g_launchers; }

@@ -72,20 +72,22 @@ constexpr int BRICK_GTAB_BYTES = 16 + 8 * BRICK_MAX_NODES + 16 * BRICK_MAX_NODES
 constexpr int BRICK_EX_STRIDE = 25;
 constexpr int BRICK_EX_ZERO = BRICK_ELEMS * BRICK_EX_STRIDE;
 
-// plan of the one-kernel unstructured gradient (pms_elem_ws.cuh): slabs of elements in index order, nodes grouped by the
-// slab of their last adjacent element, a ring of 4 slabs of per-element contributions, cross-CTA progress counters
+// plan of the one-kernel unstructured hex8 gradient (pms_elem_ws.cuh): nodes listed by the iteration in which their last
+// adjacent element is evaluated, per-node tables of scratch offsets, cross-CTA progress words
 struct WsPlanDev {
-  long long slab_elems;     // elements per slab = 32 * (compute warps of the grid) * tiles_per_warp
-  int tiles_per_warp;       // warp tiles each compute warp owns per slab
-  int nslabs;
-  const int32_t* gnodes;    // nodes sorted by (group, node id); group = slab of the node's last adjacent element
-  const long long* goff;    // [nslabs + 1]
-  const int32_t* gtab;      // [tab_w][tab_n]: ring offset (local node * 3 * ring_elems + ring index) of the k-th adjacent
-                            // element's contribution to the node at gnodes position q, ascending element order; -1 = none
-  int tab_w;                // entries per node (multiple of 4, >= the largest valence)
-  long long tab_n;          // = nnodes
-  double* ring;             // [3 * npe][4 * slab_elems]
-  int* counters;            // prog[grid] then gprog[grid] (per-CTA progress words), zeroed before the launch
+  int grid;                // CTAs the plan was built for (all co-resident)
+  int D;                   // batch j (list positions [j*grid*128, (j+1)*grid*128)) is gathered during iteration j + D
+  int nbatches;
+  int nslabs;              // slabs of 4 element iterations
+  unsigned sleep_ns;       // back-off of a CTA that has to wait for the slowest one
+  long long niter;         // iterations of every CTA = max(element iterations, nbatches + D)
+  const int32_t* lnode;    // [nbatches*grid*128] node id at list position q (-1: padding)
+  const int4* tabA;        // scratch offsets (local node * 3 * egs + element) of the node's CSR entries 0..3, -1 = none
+  const int4* tabB;        // entries 4..7
+  const int32_t* need;     // [nbatches] slabs (of 4 iterations) every CTA must have published before batch j is read
+  int* prog;               // [nslabs] CTAs through with slab s, zeroed before the launch
+  const int32_t* ovf_nodes;  // nodes with more than 8 adjacent elements: gathered by a list kernel afterwards
+  long long novf;
 };
 
 // analytic stand-in for a MeshGeometry evaluator: 0 plane (p, unit normal u), 1 sphere (centre p, R),
@@ -161,11 +163,13 @@ struct Launchers {
   bool (*grad_bricks)(cudaStream_t, const MeshDev&, const BrickDev&, int stage, const double* x, const double* w,
                       long long stride, const uint8_t* fixed, const uint8_t* node_owned, double* g, double* r_out,
                       const Reduce&, int slot, double* elem_metric, int32_t* elem_flag);
-  // one-kernel unstructured metric + gradient (element loop + lagged node gather, ring scratch in L2); `grid` = the CTA
-  // count the plan was built for; returns false when unsupported (strict build) or the launch is refused
-  bool (*grad_ws)(cudaStream_t, const MeshDev&, const WsPlanDev&, int grid, int stage, int use_ref, const double* x,
-                  const double* w, long long stride, const uint8_t* fixed, const uint8_t* node_owned, double* g, double* r_out,
-                  const Reduce&, int slot);
+  // one-kernel unstructured hex8 metric + gradient (element loop with the node gather riding on it through cp.async);
+  // returns false when unsupported (strict build, tet4, no reference mesh) or the launch is refused
+  bool (*grad_ws)(cudaStream_t, const MeshDev&, const WsPlanDev&, int stage, int use_ref, const double* x, const double* w,
+                  long long stride, const uint8_t* fixed, const uint8_t* node_owned, double* g, double* r_out, double* eg,
+                  long long egs, const Reduce&, int slot);
+  // CTAs that kernel runs with (the plan is built for this grid); 0 = not available
+  int (*grad_ws_grid)();
   // cross-rank interface sum (structured block per GPU), ascending rank order
   void (*shared_sum)(cudaStream_t, long long nshared, const int32_t* nodes, const int64_t* ptr, const int64_t* ent_pos,
                      const int32_t* ent_cnt, const double* recvbuf, double* f, int ncomp, long long stride);

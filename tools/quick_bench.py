@@ -21,6 +21,8 @@ def run(kind, nele, eps, reps=5):
     c.set_option("cache_metric", 0)
     if os.environ.get("QB_FUSED"):
         c.set_option("sgrid_fused", int(os.environ["QB_FUSED"]))
+    if os.environ.get("QB_ELEMWS"):
+        c.set_option("elem_ws", int(os.environ["QB_ELEMWS"]))
     if os.environ.get("QB_VARIANT"):
         vm, vg = os.environ["QB_VARIANT"].split(",")
         c.set_option("variant_metric_corners", int(vm)); c.set_option("variant_grad_corners", int(vg))
@@ -35,13 +37,14 @@ def run(kind, nele, eps, reps=5):
                 if it == 2: c.kernel_time_reset()
                 if what == "multi": c.total_metric_multi(stage, [0.5 * 0.5 ** k for k in range(8)]); continue
                 if what == "multi12": c.total_metric_multi(stage, [0.5 * 0.5 ** k for k in range(12)]); continue
+                if what == "multi16": c.total_metric_multi(stage, [0.5 * 0.5 ** k for k in range(16)]); continue
                 if what == "metric0": c.total_metric(stage, 0.0)
                 elif what == "metricA": c.total_metric(stage, 0.5)
                 else: c.metric_and_gradient(stage)
             fam = "gradient" if what == "mgrad" else "metric"
             ms, n = c.kernel_time_ms(fam)
             ms /= reps
-            bpn = {"metric0": 48, "metricA": 72, "mgrad": 72, "multi": 72, "multi12": 72}[what]
+            bpn = {"metric0": 48, "metricA": 72, "mgrad": 72, "multi": 72, "multi12": 72, "multi16": 72}[what]
             extra = 0 if kind == "sgrid" else (32 if kind == "hex8" else 16) * ne
             gb = (bpn * nnod + extra) / 1e9
             print(f"stage {stage} {what:8s}: {ms:8.3f} ms  {ne/ms/1e6:8.2f} Gelem/s  alg {gb/ms*1e3:7.1f} GB/s ({gb/ms*1e3/6561.6*100:5.1f}% of 6561.6)")
