@@ -38,7 +38,8 @@ sys.path.insert(0, ROOT)
 ALG_BYTES_PER_NODE_MGRAD = 72   # read x (24) + read x_ref (24) + write g (24)   [SURVEY 8(d)]
 ALG_BYTES_PER_HEX8_CONN = 32    # int32 connectivity read once per element
 ALG_BYTES_PER_TET4_CONN = 16
-FP64_INSTR_PER_HEX_MGRAD = 1282.0  # ShapeB1 metric+gradient, FP64 thread-instructions per hex (ncu inst count, profiles/)
+FP64_INSTR_PER_HEX_MGRAD = 1223.0  # ShapeB1 metric+gradient, FP64 thread-instructions per hex (static SASS count of the element
+                                   # kernel, tools/sass_mix.py; profiles/r02_traffic.json)
 
 
 def hbm_peak():
@@ -329,6 +330,13 @@ def profile_traffic(key):
             except Exception:
                 pass
     return None, None
+
+
+def tet_traffic(E):
+    """DRAM bytes of the tet4 evaluation from the ncu capture: only meaningful for the single-GPU mesh it was taken on."""
+    if E.world != 1:
+        return None, None
+    return profile_traffic("tet4_mgrad_dram_bytes_per_eval")
 
 
 # ---- headline: BASELINE config 3 ------------------------------------------------------------------------------------
@@ -634,7 +642,8 @@ def bench_tet4(E, args, n=119):
                         f"cg_s ghost exchange per CG iteration" if world > 1 else "single GPU",
            "n_gpus": world, "scaling": "strong", "value": nel_glob / (ms_step * 1e-3) / 1e6, "unit": "Melem/s", "ms_per_step": ms_step,
            "steps": steps, "kernel_ms_per_eval": fam["gradient"], "launches_per_step": launches,
-           "roofline": roofline_dict(alg_bytes, fam["gradient"], "k_elem_pipe<tet4,ShapeB1,grad> + k_grad_gather_csr (this rank's part)"),
+           "roofline": roofline_dict(alg_bytes, fam["gradient"], "k_elem_pipe<tet4,ShapeB1,grad> + k_grad_gather_csr (this rank's part)",
+                                     *tet_traffic(E)),
            "cg": cg, "check": {"total_metric": mtot, "n_invalid": int(ninv)}, "setup_s": t_setup}
     ctx.close()
     return out
@@ -880,11 +889,11 @@ def run_ours(args):
     fp64_peak = 148 * 64 * (clocks.get("sm_mhz") or 1965) * 1e6
     roofline = roofline_dict(H["alg_bytes"], kernel_ms, "k_elem_pipe<hex8,ShapeB1,grad> + k_grad_gather_csr (one evaluation)",
                              H["traffic"], H["traffic_source"],
-                             {"note": "the evaluation is FP64-pipe-bound (1282 FP64 instr/hex vs 64 lanes/clk/SM), see DESIGN.md",
+                             {"note": f"the evaluation is FP64-pipe-bound ({FP64_INSTR_PER_HEX_MGRAD:.0f} FP64 instr/hex vs 64 lanes/clk/SM), see DESIGN.md",
                               "fp64_pipe": {"achieved_ginstr_s": fp64_instr / (kernel_ms * 1e-3) / 1e9, "peak_ginstr_s": fp64_peak / 1e9,
                                             "frac": fp64_instr / (kernel_ms * 1e-3) / fp64_peak,
-                                            "note": f"{FP64_INSTR_PER_HEX_MGRAD:.0f} FP64 thread-instructions per hex is the ncu count of the profiles/ "
-                                                    f"capture, not re-measured in this run; whole evaluation incl. the HBM-bound gather pass"}})
+                                            "note": f"{FP64_INSTR_PER_HEX_MGRAD:.0f} FP64 thread-instructions per hex is the static SASS count of the element kernel "
+                                                    f"(profiles/r02_traffic.json), not re-measured in this run; whole evaluation incl. the HBM-bound gather pass"}})
 
     # ---- CPU baseline on this box's host cores, bounded sample; the same oracle context then checks the GPU ----------
     cpu_baseline = None

@@ -316,7 +316,7 @@ void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t
   }
 }
 
-// total_metric at nb (8, 12 or 16) step lengths in one pass (hex meshes, one block).  Returns false when the kernel is
+// total_metric at nb (8, 10, 12, 14 or 16) step lengths in one pass (hex meshes, one block).  Returns false when the kernel is
 // not available for this mesh / build; the caller then evaluates one alpha at a time.
 bool op_total_metric_multi(pms_ctx* c, int stage, int nb, const double* alphas, double* mtot, uint64_t* ninv) {
   if (c->dev_blocks.size() != 1 || c->keep_elem || c->strict_fp || nb > pmsk::MULTI_ALPHA_NB) return false;
@@ -961,7 +961,7 @@ struct Driver {
     // previous search's trials + 1 more + the quadratic fit's a1; a search that outruns the batch gets a batch of 8 more
     constexpr int NBMAX = pmsk::MULTI_ALPHA_NB;
     const int need = c->spec_prev > 0 ? c->spec_prev + 2 : 12, done = spec_cur;
-    const int nb = done > 0 ? 8 : (need <= 8 ? 8 : (need <= 12 ? 12 : NBMAX));
+    const int nb = done > 0 ? 8 : std::min(NBMAX, std::max(8, (need + 1) & ~1));  // kernels for 8, 10, 12, 14, 16 step lengths
     double al[NBMAX], m[NBMAX];
     uint64_t n[NBMAX];
     double a = alpha;
@@ -2273,7 +2273,7 @@ int pms_total_metric_multi(pms_ctx* c, int stage, int nalpha, const double* alph
   for (int k0 = 0; k0 < nalpha;) {
     double al[NBMAX], m[NBMAX];
     uint64_t n[NBMAX];
-    const int left = nalpha - k0, nb = left > 12 ? NBMAX : (left > 8 ? 12 : 8), cnt = std::min(nb, left);
+    const int left = nalpha - k0, nb = std::min(NBMAX, std::max(8, (left + 1) & ~1)), cnt = std::min(nb, left);
     for (int k = 0; k < nb; k++) al[k] = alphas[k0 + std::min(k, cnt - 1)];
     if (!op_total_metric_multi(c, stage, nb, al, m, n))  // tet4 / strict build / multi-block: one pass per alpha
       for (int k = 0; k < cnt; k++) op_total_metric(c, stage, al[k], &m[k], &n[k]);

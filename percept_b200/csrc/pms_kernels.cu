@@ -1294,25 +1294,27 @@ static void launch_metric_multi1(cudaStream_t st, const MeshDev& m, int stage, c
 static bool launch_metric_multi(cudaStream_t st, const MeshDev& m, int stage, int use_ref, int nb, const double* x, const double* s,
                                 const double* w, long long stride, const double* alphas, const Reduce& R, int slot,
                                 const uint8_t* fixed) {
-  if (STRICT || m.kind == KIND_TET4 || (stage != 0 && !use_ref) || (nb != 8 && nb != 12 && nb != 16)) return false;
+  if (STRICT || m.kind == KIND_TET4 || (stage != 0 && !use_ref) || (nb < 8 || nb > 16 || (nb & 1))) return false;  // kernels for 8, 10, 12, 14, 16
   // structured blocks: TMA-staged tile kernel (pms_sgrid_tile.cuh)
   // (ShapeB1 only: the cheap untangle polynomial runs faster in the per-thread pipelined kernel, 1.73 vs 1.97 ms)
   if (m.kind == KIND_SGRID && stage == 1 && g_sgrid_tile && launch_sgrid_tile_multi(st, m, stage, nb, x, s, w, stride, fixed, alphas, R, slot))
     return true;
   if (m.kind == KIND_SGRID) {
-    if (nb == 8)
-      launch_metric_multi1<FL_SGRID, 8>(st, m, stage, x, s, w, stride, alphas, R, slot);
-    else if (nb == 12)
-      launch_metric_multi1<FL_SGRID, 12>(st, m, stage, x, s, w, stride, alphas, R, slot);
-    else
-      launch_metric_multi1<FL_SGRID, 16>(st, m, stage, x, s, w, stride, alphas, R, slot);
+    switch (nb) {
+      case 8: launch_metric_multi1<FL_SGRID, 8>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+      case 10: launch_metric_multi1<FL_SGRID, 10>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+      case 12: launch_metric_multi1<FL_SGRID, 12>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+      case 14: launch_metric_multi1<FL_SGRID, 14>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+      default: launch_metric_multi1<FL_SGRID, 16>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+    }
   } else {
-    if (nb == 8)
-      launch_metric_multi1<FL_HEX8, 8>(st, m, stage, x, s, w, stride, alphas, R, slot);
-    else if (nb == 12)
-      launch_metric_multi1<FL_HEX8, 12>(st, m, stage, x, s, w, stride, alphas, R, slot);
-    else
-      launch_metric_multi1<FL_HEX8, 16>(st, m, stage, x, s, w, stride, alphas, R, slot);
+    switch (nb) {
+      case 8: launch_metric_multi1<FL_HEX8, 8>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+      case 10: launch_metric_multi1<FL_HEX8, 10>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+      case 12: launch_metric_multi1<FL_HEX8, 12>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+      case 14: launch_metric_multi1<FL_HEX8, 14>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+      default: launch_metric_multi1<FL_HEX8, 16>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+    }
   }
   return true;
 }

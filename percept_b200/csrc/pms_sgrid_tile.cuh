@@ -734,7 +734,9 @@ static bool launch_sgrid_tile_multi(cudaStream_t st, const MeshDev& m, int stage
                                     int slot) {
   if (STRICT || !s || !sgrid_tile_ok(m, x, s, w, stride, fixed)) return false;
   if (nb == 8) return launch_sgrid_tile_multi1<8>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
+  if (nb == 10) return launch_sgrid_tile_multi1<10>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
   if (nb == 12) return launch_sgrid_tile_multi1<12>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
+  if (nb == 14) return launch_sgrid_tile_multi1<14>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
   if (nb == 16) return launch_sgrid_tile_multi1<16>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
   return false;
 }

@@ -5,7 +5,7 @@ import numpy as np
 import percept_b200 as pb
 from percept_b200 import fixtures as fx
 
-def run(kind, nele, eps, reps=5):
+def run(kind, nele, eps, reps=int(os.environ.get("QB_REPS", "5"))):
     nn = nele + 1
     W = fx.cube(nn); X = fx.perturb_rand(W, nn, eps / nele, 1)
     c = pb.create()
