@@ -77,7 +77,11 @@ const char* pms_last_error(const pms_ctx* ctx);
  *                  from) instead of f'(x_old).  0 = the reference's literal pass sequence.
  *  "smooth_surfaces"  (PerceptMesh::get_smooth_surfaces) default 0, see the surface smoothing hooks below
  *  "keep_element_metrics"  1 = metric passes also store per-element values for pms_get_element_metrics
- *  "variant_metric_corners" / "variant_grad_corners"  kernel variants (tuning aid)             */
+ *  "variant_metric_corners" / "variant_grad_corners"  kernel variants (tuning aid)
+ *  "sgrid_fused"   default 1: structured blocks use the one-pass tile kernels (TMA-staged node planes, in-CTA ordered
+ *                  gather, pms_sgrid_tile.cuh); 0 = element pass + per-cell scratch + node gather.  Same bits either way.
+ *  "elem_ws"       default 0: 1 = unstructured hex8 gradient in one kernel (node gather riding on the element loop,
+ *                  pms_elem_ws.cuh); same bits as the two passes, measured slower (profiles/r02_elem_gather.md)         */
 int pms_set_option(pms_ctx* ctx, const char* key, double value);
 
 /* ---- mesh definition ---------------------------------------------------- */
