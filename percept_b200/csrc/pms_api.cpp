@@ -275,6 +275,28 @@ double op_dot(pms_ctx* c, const char* x, const char* y) {
 void halo_exchange(pms_ctx* c, const char* name);
 void interface_sum(pms_ctx* c, DField& F);
 
+// tet4 meshes with the reference mesh: W^-1 and det W per element, computed once per version of coordinates_NM1; the
+// element kernels then read 10 coalesced values instead of gathering 4 reference vertices (12 scattered loads)
+void ensure_tetref(pms_ctx* c) {
+  if (c->structured || c->topo != 4 || c->dev_blocks.empty()) return;
+  pmsk::MeshDev& m = c->dev_blocks[0];
+  if (c->strict_fp || !c->tet_ref_cache || !c->use_ref_mesh || c->E < 1) {
+    m.tetref = nullptr;
+    return;
+  }
+  DField& W = c->field("coordinates_NM1");
+  if (!c->d_tetref) c->d_tetref = dalloc<double>((size_t)10 * c->Epad);
+  if (c->tetref_wv != W.version) {
+    Timed t(c, FAM_EDGE);
+    m.tetref = nullptr;
+    c->L->tet_ref(c->stream, m, W.d, c->Npad, c->d_tetref, c->Epad);
+    check_launch(c, "tet_ref");
+    c->tetref_wv = W.version;
+  }
+  m.tetref = c->d_tetref;
+  m.tetref_stride = c->Epad;
+}
+
 // total_metric(alpha), Def.hpp:330-388, without materialising x + alpha*s
 void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t* ninv, bool count_eval = true) {
   (c->strict_fp ? pms_strict::set_variant : pms_fast::set_variant)(c->var_metric, c->var_grad, c->sgrid_fused ? 1 : 0);  // the switches live in the kernel TU: apply this ctx's
@@ -293,6 +315,7 @@ void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t
   }
   const int nb = (int)c->dev_blocks.size();
   if (nb > pms_ctx::NSLOT) throw PmsError(PMS_ERR_ARG, "too many structured blocks in one ctx");
+  ensure_tetref(c);
   for (int b = 0; b < nb; b++) {
     Timed t(c, FAM_METRIC);
     c->L->metric(c->stream, c->dev_blocks[b], stage, c->use_ref_mesh ? 1 : 0, X.d, with_s ? S.d : nullptr, W.d, c->Npad,
@@ -751,6 +774,7 @@ void op_gradient(pms_ctx* c, int stage, double* mtot, uint64_t* ninv, bool write
   }
   if (!fused_ok) {
     ensure_eg(c);
+    ensure_tetref(c);
     for (int b = 0; b < nb; b++) {
       Timed t(c, FAM_GRADIENT, 2);
       c->L->grad_elements(c->stream, c->dev_blocks[b], stage, use_ref, X.d, W.d, c->Npad, c->d_eg, c->Epad, c->R, b,
@@ -1372,7 +1396,7 @@ void pms_destroy(pms_ctx* c) {
                     c->d_csr_ptr,   c->d_csr_ent,   c->d_grp_ptr,    c->d_grp_nodes,  c->d_eg,       c->d_elem_metric,
                     c->d_elem_flag, c->R.partial_d, c->R.partial_u,  c->R.ticket,     c->R.out_d,    c->R.out_u,
                     c->d_send_nodes, c->d_recv_nodes, c->d_send_buf, c->d_recv_buf,   c->d_coll, c->d_skip, c->d_csr_ent32, c->d_if_nodes, c->d_sh_nodes, c->d_sh_cnt, c->d_sh_ptr, c->d_sh_pos,
-                    c->d_if_send, c->d_if_recv, c->d_seam, (void*)c->ws.lnode, (void*)c->ws.tabA, (void*)c->ws.tabB, (void*)c->ws.need, c->ws.prog, (void*)c->ws.ovf_nodes};
+                    c->d_if_send, c->d_if_recv, c->d_seam, c->d_tetref, (void*)c->ws.lnode, (void*)c->ws.tabA, (void*)c->ws.tabB, (void*)c->ws.need, c->ws.prog, (void*)c->ws.ovf_nodes};
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->h_out_d) cudaFreeHost(c->h_out_d);
@@ -1432,6 +1456,9 @@ int pms_set_option(pms_ctx* c, const char* key, double v) {
   } else if (k == "variant_grad_corners") {
     c->var_grad = (int)v;
     pms_fast::set_variant(c->var_metric, c->var_grad);
+    invalidate_cache(c);
+  } else if (k == "tet_ref_cache") {  // 1 (default): tet4 kernels read the cached reference part per element; 0: gather the reference vertices
+    c->tet_ref_cache = v != 0;
     invalidate_cache(c);
   } else if (k == "elem_ws") {  // 1: one-kernel unstructured gradient (element loop + lagged gather); 0 (default): two passes
     c->elem_ws = v != 0;

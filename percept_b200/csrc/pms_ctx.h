@@ -77,6 +77,10 @@ struct pms_ctx {
   int64_t *d_grp_ptr = nullptr, *d_grp_nodes = nullptr;
   long long n_groups = 0;
   double* d_eg = nullptr;  // element-gradient scratch [3*npe][Epad]
+  // tet4: reference part per element (W^-1, det W), rebuilt when coordinates_NM1 changes (pms_device.cuh tet_metric_cached)
+  double* d_tetref = nullptr;
+  uint64_t tetref_wv = ~0ull;
+  bool tet_ref_cache = true;
   // one-kernel unstructured gradient (pms_elem_ws.cuh)
   pmsk::WsPlanDev ws{};
   bool ws_built = false, ws_failed = false, elem_ws = false;  // (off by default: measured slower than the two passes)

@@ -178,6 +178,124 @@ PMS_DI double element_metric(const double (&vc)[8][3], const double (&vo)[8][3],
 }
 
 // ---------------------------------------------------------------------------------------------
+// tet4 with the reference-mesh part cached per element: a tet has ONE corner Jacobian (JacobianUtil.cpp:388-396), so
+// W^-1 (9 values) and det W depend on coordinates_NM1 only and are computed once per run by k_tet_ref — the very
+// operations of corner_jacobian + matrix_inverse below — instead of gathering the 4 reference vertices (12 scattered
+// 8-byte loads per tet and pass; the tet kernels are L1/LSU-bound on exactly those gathers).  ref[v/3][v%3], v = 0..8:
+// WI row-major, v = 9: det W.  Same expression order as element_metric / element_grad_metric<FL_TET4, STAGE, true>.
+// ---------------------------------------------------------------------------------------------
+PMS_DI void tet_reference(const double (&vo)[8][3], double (&ref)[10]) {
+  double W[3][3], detW, WI[3][3];
+  corner_jacobian<FL_TET4>(vo, 0, W, detW);
+  matrix_inverse(W, detW, WI);
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) ref[a * 3 + b] = WI[a][b];
+  ref[9] = detW;
+}
+
+template <int STAGE, bool GRAD>
+PMS_DI double tet_metric_cached(const double (&vc)[8][3], const double (&ref)[8][3], bool& valid, double (&grad)[8][3]) {
+  valid = true;
+  double A[3][3], detA;
+  corner_jacobian<FL_TET4>(vc, 0, A, detA);
+  const double detW = ref[3][0];
+  if (detA <= 0.0) valid = false;
+  if (GRAD) {
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) grad[a][r] = 0.0;
+  }
+  double dM[3][3];
+  double m = 0.0;
+  bool have = false;
+  if (STAGE == 0) {
+    const double vv = BETA_MULT * detW - detA;
+    const double vv1 = (vv > 0.0 ? vv : 0.0);
+    m = vv1 * vv1;
+    if (GRAD && vv > 0.0) {
+      have = true;
+      double TA[3][3];
+      transpose_adj(A, TA);
+      const double s = -2.0 * vv;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) dM[a][b] = s * TA[a][b];
+    }
+  } else if (detA > 0.0) {
+    have = true;
+    double WI[3][3], T[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) WI[a][b] = ref[a][b];
+    matrix_product(A, WI, T);
+    const double d = detA / detW;
+    const double f = sqrt(sqr_frobenius(T));
+    const double den = FAC_3SQRT3 * d;
+    const double shape_metric = (f * f * f) / den - 1.0;
+    m = shape_metric * detW;
+    if (GRAD) {
+      const double norm = f;
+      const double iden = 1.0 / den;
+      const double s1 = (3 * norm * iden);
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) dM[a][b] = s1 * T[a][b];
+      const double norm_cube = norm * norm * norm;
+      double TAT[3][3];
+      transpose_adj(T, TAT);
+      const double s2 = (norm_cube * iden / d);
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) dM[a][b] -= s2 * TAT[a][b];
+      double tmp[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) {  // DenseMatrix operator*, DenseMatrix.hpp:502-533 (k = 0,2,1)
+          double t = dM[a][0] * WI[b][0];
+          t += dM[a][2] * WI[b][2];
+          t += dM[a][1] * WI[b][1];
+          tmp[a][b] = t;
+        }
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) dM[a][b] = tmp[a][b] * detW;
+    }
+  }
+  double val = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) val += m;
+  if (GRAD && have) {  // grad_util_tet_3d, JacobianUtil.cpp:215-243, then grad = ((G+G)+G)+G over the 4 identical corners
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      double G0 = 0.0, G1 = 0.0, G2 = 0.0, G3 = 0.0;
+      G1 += dM[r][0] * (+1);
+      G0 += dM[r][0] * (-1);
+      G2 += dM[r][1] * (+2.0 * ISQRT3);
+      G1 += dM[r][1] * (-1.0 * ISQRT3);
+      G0 += dM[r][1] * (-1.0 * ISQRT3);
+      G3 += dM[r][2] * (+3.0 * ISQRT6);
+      G2 += dM[r][2] * (-1.0 * ISQRT6);
+      G1 += dM[r][2] * (-1.0 * ISQRT6);
+      G0 += dM[r][2] * (-1.0 * ISQRT6);
+      grad[0][r] = ((G0 + G0) + G0) + G0;
+      grad[1][r] = ((G1 + G1) + G1) + G1;
+      grad[2][r] = ((G2 + G2) + G2) + G2;
+      grad[3][r] = ((G3 + G3) + G3) + G3;
+    }
+  }
+  return val;
+}
+
+// ---------------------------------------------------------------------------------------------
 // element metric + gradient.  grad[a][r] = d(metric)/d(x_a,r) following grad_metric + grad_util;
 // returns the metric value as total_metric would compute it (scaled by detW for ShapeB1).
 // In smoothing mode corners with detA<=0 contribute nothing and the caller drops the whole

@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
   // gradient of a hex on the fast path: vertices are read IN PLACE from shared memory (frees 96 registers for the
   // 24 gradient accumulators + interleaved corner chains), so the prefetch targets the other of two buffers
   constexpr bool INPLACE = FAST && GRAD && !WITH_S;
+  constexpr bool TETREF = FL == FL_TET4 && USE_REF;  // reference part cached per element (when the mesh carries it)
   constexpr int NVAL = NN * 3 * (WITH_S ? 3 : 2);
   extern __shared__ double sm[];  // [INPLACE ? 2 : 1][NVAL][NTP]
   const int tid = threadIdx.x;
@@ -639,9 +640,13 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
 #pragma unroll
         for (int r = 0; r < 3; r++) {
           cp_async8(slot_in(buf, 0, a, r), &x[r * stride + nid]);
-          cp_async8(slot_in(buf, 1, a, r), &w[r * stride + nid]);
+          if (!TETREF || !m.tetref) cp_async8(slot_in(buf, 1, a, r), &w[r * stride + nid]);
           if (WITH_S) cp_async8(slot_in(buf, 2, a, r), &s[r * stride + nid]);
         }
+      }
+      if (TETREF && m.tetref) {  // the element's cached reference part: 10 coalesced values instead of 12 scattered ones
+#pragma unroll
+        for (int v = 0; v < 10; v++) cp_async8(slot_in(buf, 1, v / 3, v % 3), &m.tetref[(long long)v * m.tetref_stride + m.elem_off + e_nxt]);
       }
       if (WITH_S) bits_nxt = m.elem_fixed_bits[m.elem_off + e_nxt];
     }
@@ -692,6 +697,8 @@ __global__ void __launch_bounds__(NTP, (GRAD ? PIPE_MINB_GRAD : PIPE_MINB_METRIC
       mm = hex_shapeb1_metric_ilp(vc, vo, valid);
     } else if (FAST) {
       mm = hex_metric_fast<STAGE, GRAD>(vc, vo, valid, grad);
+    } else if (TETREF && m.tetref) {
+      mm = tet_metric_cached<STAGE, GRAD>(vc, vo, valid, grad);
     } else if (GRAD) {
       mm = element_grad_metric<FL, STAGE, USE_REF>(vc, vo, valid, grad);
     } else {
@@ -2202,6 +2209,27 @@ static void launch_surf_normals(cudaStream_t st, long long n, const int32_t* nod
   if (n > 0) k_surf_normals<<<(unsigned)((n + NT - 1) / NT), NT, 0, st>>>(n, nodes, sid, surfs, x, out, stride);
 }
 
+// tet4: W^-1 and det W of every element from the reference coordinates (once per run; tet_reference, pms_device.cuh)
+__global__ void __launch_bounds__(NT) k_tet_ref(const MeshDev m, const double* __restrict__ w, const long long stride,
+                                                double* __restrict__ out, const long long out_stride) {
+  const long long e = (long long)blockIdx.x * NT + threadIdx.x;
+  if (e >= m.nelems) return;
+  double vo[8][3], ref[10];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const long long nid = __ldg(&m.conn[(long long)a * m.conn_stride + e]);
+#pragma unroll
+    for (int r = 0; r < 3; r++) vo[a][r] = __ldg(&w[r * stride + nid]);
+  }
+  tet_reference(vo, ref);
+#pragma unroll
+  for (int v = 0; v < 10; v++) out[(long long)v * out_stride + m.elem_off + e] = ref[v];
+}
+static void launch_tet_ref(cudaStream_t st, const MeshDev& m, const double* w, long long stride, double* out, long long out_stride) {
+  if (m.kind == KIND_TET4 && m.nelems > 0)
+    k_tet_ref<<<(unsigned)((m.nelems + NT - 1) / NT), NT, 0, st>>>(m, w, stride, out, out_stride);
+}
+
 static void launch_elem_fixed_bits(cudaStream_t st, const MeshDev& m, const uint8_t* fixed, uint8_t* bits) {
   if (m.kind == KIND_SGRID)
     k_elem_fixed_bits<FL_SGRID><<<elem_grid<FL_SGRID>(m), NT, 0, st>>>(m, fixed, bits);
@@ -2216,7 +2244,7 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_group_sum, launch_axpby,         launch_axpbypgz,    launch_set,
                                       launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_cg_s_update_dots, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,
-                                      launch_unpack,    launch_elem_fixed_bits, launch_grad_bricks, launch_elem_ws, elem_gather_grid, launch_shared_sum,
+                                      launch_unpack,    launch_elem_fixed_bits, launch_tet_ref, launch_grad_bricks, launch_elem_ws, elem_gather_grid, launch_shared_sum,
                                       launch_metric_multi, launch_refine_sgrid, launch_surf_project, launch_surf_snap, launch_surf_normals};
 
 const Launchers* launchers() { return &g_launchers; }

@@ -26,6 +26,8 @@ struct MeshDev {
   const int64_t* csr_ptr;          // unstructured node->element CSR
   const int64_t* csr_ent;          // entries elem*8+local, ascending
   const int32_t* csr_ent32;        // same, 32-bit (when nelems*8 < 2^31): halves the gather's index traffic
+  const double* tetref;            // tet4: cached reference part per element, tetref[v*tetref_stride + e], v = 0..8 W^-1, 9 det W (null: gather the reference vertices)
+  long long tetref_stride;
 };
 
 constexpr int REDUCE_MAX_NV = 32;   // doubles one grid reduction can carry
@@ -159,6 +161,8 @@ struct Launchers {
   void (*unpack)(cudaStream_t, double* f, long long stride, int ncomp, const int32_t* nodes, long long count, const double* buf);
   // per-element bit mask of fixed vertices
   void (*elem_fixed_bits)(cudaStream_t, const MeshDev&, const uint8_t* fixed, uint8_t* bits);
+  // tet4: reference-mesh part of every element (W^-1, det W) from the reference coordinates w -> out[v*out_stride + e]
+  void (*tet_ref)(cudaStream_t, const MeshDev&, const double* w, long long stride, double* out, long long out_stride);
   // scratch-free hex8 gradient over bricks (default build only); returns false when unsupported
   bool (*grad_bricks)(cudaStream_t, const MeshDev&, const BrickDev&, int stage, const double* x, const double* w,
                       long long stride, const uint8_t* fixed, const uint8_t* node_owned, double* g, double* r_out,

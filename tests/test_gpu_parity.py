@@ -404,7 +404,8 @@ def test_multi_alpha_metric_matches_single_evaluations_and_oracle(kind, eps):
     for stage in (0, 1):
         before = g.launch_count()
         mg, ng = g.total_metric_multi(stage, alphas)
-        assert g.launch_count() - before == (1 if kind != "tet4" else len(alphas))  # 14 alphas = one pass of 16
+        # 14 alphas = one pass of 14; tet4: one pass per alpha (+ once per run the reference cache of its elements)
+        assert g.launch_count() - before == (1 if kind != "tet4" else len(alphas) + (1 if stage == 0 else 0))
         g.set_option("cache_metric", 0)
         for k, a in enumerate(alphas):
             mo, no = o.total_metric(stage, a)
@@ -592,3 +593,35 @@ def test_line_search_on_its_own(kind, strict):
     m0, _ = g.total_metric(1, 0.0)
     m1, _ = g.total_metric(1, out[0])
     assert m1 < m0
+
+
+@pytest.mark.parametrize("stage", [0, 1])
+def test_tet_reference_cache_matches_gathered_reference_and_follows_the_reference_mesh(stage):
+    """tet4: W^-1 and det W cached per element (k_tet_ref) instead of gathering the 4 reference vertices in every pass.
+    Same operations, so the results agree to rounding with the gathering kernels and with the oracle; a new reference mesh
+    (coordinates_NM1 uploaded again) must be picked up."""
+    nele = 12
+    X, W = meshes.perturbed_coords(nele, 1.0 if stage == 0 else 0.25)
+    a = meshes.build(pb.api, "tet4", nele, X, W, True, {"cache_metric": 0, "tet_ref_cache": 1})
+    b = meshes.build(pb.api, "tet4", nele, X, W, True, {"cache_metric": 0, "tet_ref_cache": 0})
+    o = meshes.build(oracle, "tet4", nele, X, W, True, {"real_is_double": 1})
+    s = meshes.seeded_field(a.num_nodes_local, 5, 0.02 / nele)
+    for c in (a, b, o):
+        c.upload("cg_s", s)
+
+    def compare():
+        for alpha in (0.0, 0.5):
+            (ma, na), (mb, nb), (mo, no) = a.total_metric(stage, alpha), b.total_metric(stage, alpha), o.total_metric(stage, alpha)
+            assert na == nb == no
+            assert abs(ma - mb) <= 1e-13 * abs(mb) and abs(ma - mo) <= 1e-12 * abs(mo)
+        (ma, na), (mb, nb), (mo, no) = a.metric_and_gradient(stage), b.metric_and_gradient(stage), o.metric_and_gradient(stage)
+        assert na == nb == no and abs(ma - mo) <= 1e-12 * abs(mo)
+        ga, gb, go = a.download("cg_g"), b.download("cg_g"), o.download("cg_g")
+        scale = np.max(np.abs(go))
+        assert np.max(np.abs(ga - gb)) <= 1e-13 * scale and np.max(np.abs(ga - go)) <= 1e-12 * scale
+
+    compare()
+    W2 = W * np.array([1.0, 1.3, 0.8])[:, None] if W.shape[0] == 3 else W * np.array([1.0, 1.3, 0.8])
+    for c in (a, b, o):
+        c.upload("coordinates_NM1", W2)
+    compare()
