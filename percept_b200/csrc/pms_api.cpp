@@ -1821,7 +1821,9 @@ int pms_commit(pms_ctx* c) {
   }
 
   // reduction scratch: partial slots for the largest grid any kernel launches
-  long long maxb = 148 * 16;
+  int nsm_dev = 148;
+  if (cudaDeviceGetAttribute(&nsm_dev, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess || nsm_dev < 1) nsm_dev = 148;
+  long long maxb = (long long)nsm_dev * 16;  // the persistent kernels launch at most SMs x 16 CTAs
   for (auto& m : c->dev_blocks) {
     long long nb = m.kind == pmsk::KIND_SGRID
                        ? (long long)((m.ni + 30) / 32) * ((m.nj + 2) / 4) * ((m.nk + 0) / 2 + 1)

@@ -27,6 +27,9 @@
 #ifndef PMS_RSQRT_CUBIC
 #define PMS_RSQRT_CUBIC 1
 #endif
+#ifndef PMS_CORNER_ORDER
+#define PMS_CORNER_ORDER 1  // Gray code: 1.3 % faster element pass than the natural order (gpurun_out/ab_co.log)
+#endif
 #ifndef PMS_NO_OK_SELECT
 #define PMS_NO_OK_SELECT 1  // ShapeB1 gradient: no per-corner selects on detA > 0 (the element-level rule covers them)
 #endif
@@ -144,8 +147,13 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
       for (int r = 0; r < 3; r++) grad[a][r] = 0.0;
   }
 #pragma unroll
-  for (int c = 0; c < 8; c++) {
-    if (c == 4) mid();
+  for (int cc = 0; cc < 8; cc++) {
+    if (cc == 4) mid();
+    // corner visiting order (PMS_CORNER_ORDER): 0 natural; 1 Gray code (consecutive corners share an edge, so every edge
+    // accumulator is completed as early as possible); 2 k-pairs first.  The edge accumulators are keyed on the corner's
+    // position (lo/hi), so the order only changes which of an edge's two corners is visited first.
+    constexpr int ORD[3][8] = {{0, 1, 2, 3, 4, 5, 6, 7}, {0, 1, 3, 2, 6, 7, 5, 4}, {0, 4, 1, 5, 3, 7, 2, 6}};
+    const int c = ORD[PMS_CORNER_ORDER][cc];
     double a0[3], a1[3], a2[3], w0[3], w1[3], w2[3];
     corner_edge<0>(vc, c, a0);
     corner_edge<1>(vc, c, a1);
@@ -249,12 +257,17 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
         const int lo = c & ~(1 << s), hi = lo | (1 << s);
         if (PMS_GRAD_EDGE_ACC) {
           const int ei = ((lo >> (s + 1)) << s) | (lo & ((1 << s) - 1));  // lo with bit s squeezed out
+          // first of the edge's two corners in the visiting order?
+          bool first = true;
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+            if (q < cc && ORD[PMS_CORNER_ORDER][q] == (c ^ (1 << s))) first = false;
 #pragma unroll
           for (int r = 0; r < 3; r++) {
             if (STAGE == 0)
-              E[s][ei][r] = (c == lo) ? nk2 * K[s][r] : fma(nk2, K[s][r], E[s][ei][r]);
+              E[s][ei][r] = first ? nk2 * K[s][r] : fma(nk2, K[s][r], E[s][ei][r]);
             else
-              E[s][ei][r] = fma(nk2, K[s][r], (c == lo) ? k1 * Tp[r][s] : fma(k1, Tp[r][s], E[s][ei][r]));
+              E[s][ei][r] = fma(nk2, K[s][r], first ? k1 * Tp[r][s] : fma(k1, Tp[r][s], E[s][ei][r]));
           }
         } else {
 #pragma unroll

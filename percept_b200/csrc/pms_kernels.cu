@@ -192,11 +192,10 @@ __device__ __forceinline__ bool element_of_tile(const MeshDev& m, const long lon
   }
 }
 
-constexpr int PERSIST_BLOCKS = 148 * 8;  // 148 SMs x up to 8 CTAs; tiles beyond that are strided
 template <int FL>
 static unsigned elem_grid(const MeshDev& m) {
-  const long long nt = num_tiles<FL>(m);
-  return (unsigned)(nt < PERSIST_BLOCKS ? (nt < 1 ? 1 : nt) : PERSIST_BLOCKS);
+  const long long nt = num_tiles<FL>(m), cap = (long long)sm_count() * 8;  // SMs x up to 8 CTAs; tiles beyond that are strided
+  return (unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap);
 }
 
 // position of local vertex a in the register array: Exodus hex8 order is permuted to structured numbering on the
@@ -333,7 +332,7 @@ static dim3 corner_grid(const MeshDev& m) {
     return dim3((unsigned)(((m.ni - 1 + CT_I - 1) / CT_I) * ((m.nj - 1 + CT_J - 1) / CT_J)),
                 (unsigned)((m.nk - 1 + CT_KCHUNK - 1) / CT_KCHUNK), 1);
   const long long nt = (m.nelems + 31) / 32;
-  const long long cap = 148LL * 16;
+  const long long cap = (long long)sm_count() * 16;
   return dim3((unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), 1, 1);
 }
 
@@ -520,7 +519,7 @@ static dim3 quad_grid(const MeshDev& m) {
     return dim3((unsigned)(((m.ni - 1 + QT_I - 1) / QT_I) * ((m.nj - 1 + QT_J - 1) / QT_J)),
                 (unsigned)((m.nk - 1 + QT_KCHUNK - 1) / QT_KCHUNK), 1);
   const long long nt = (m.nelems + 31) / 32;
-  const long long cap = 148LL * 16;
+  const long long cap = (long long)sm_count() * 16;
   return dim3((unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), 1, 1);
 }
 
@@ -1096,7 +1095,7 @@ static bool launch_grad_bricks(cudaStream_t st, const MeshDev& m, const BrickDev
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, nthreads, BRICK_SMEM);
     if (bps < 1) bps = 1;
   }
-  const long long cap = 148LL * bps;
+  const long long cap = (long long)sm_count() * bps;
   const unsigned grid = (unsigned)(B.nbricks < cap ? (B.nbricks < 1 ? 1 : B.nbricks) : cap);
   kern<<<grid, nthreads, BRICK_SMEM, st>>>(m, B, x, w, stride, g, rout, R, slot);
   if (B.ncomb > 0) k_brick_combine<<<(unsigned)((B.ncomb + NT - 1) / NT), NT, 0, st>>>(B, fixed, owned, g, rout, stride);
@@ -1180,7 +1179,7 @@ static void launch_metric_occ(cudaStream_t st, const MeshDev& m, const double* x
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
   const long long nt = num_ptiles<FL>(m);
-  const long long cap = 148LL * blocks_per_sm;
+  const long long cap = (long long)sm_count() * blocks_per_sm;
   kern<<<(unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), NTP, smem, st>>>(m, x, s, w, stride, alpha, R, slot);
 }
 
@@ -1646,7 +1645,7 @@ static void launch_group_sum(cudaStream_t st, long long ng, const int64_t* gptr,
 // ------------------------------------------------------------------------------------------------
 static inline unsigned blas_blocks(long long n) {
   long long b = (n + NT - 1) / NT;
-  const long long cap = 148LL * 16;  // 148 SMs x resident CTAs; grid-stride beyond that
+  const long long cap = (long long)sm_count() * 16;  // SMs x resident CTAs; grid-stride beyond that
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 

@@ -68,6 +68,46 @@ int main() {
     EXPECT_EQ(ReferenceMeshSmootherConjugateGradientImpl<StructuredGrid>::parallel_count_invalid_elements(&eMesh), (size_t)391365);
     std::printf("total_metric_and_gradient: |g|_smooth-golden ok, mtot=%.6e n_invalid=%zu\n", (double)mtot, n_invalid);
   }
+  {  // the same test on the STK side (HeavyTestMeshSmoother.cpp:1376-1404 runs the STK hex8 mesh of the same perturbed
+     // cube and expects the same numbers): unstructured hex8 in Exodus order through the C++ facade, no Python in between
+    const unsigned nele = 100, nn = nele + 1;
+    const size_t N = (size_t)nn * nn * nn;
+    std::vector<double> w(3 * N), x;
+    const double width[3] = {1, 1, 1}, offset[3] = {0, 0, 0};
+    pms_fixture_cube(nn, nn, nn, width, offset, w.data());
+    x = w;
+    pms_fixture_perturb_rand(nn, nn, nn, 1.0 / (double)nele, 1, x.data());
+    std::vector<int32_t> conn;
+    conn.reserve((size_t)8 * nele * nele * nele);
+    for (unsigned k = 0; k < nele; k++)
+      for (unsigned j = 0; j < nele; j++)
+        for (unsigned i = 0; i < nele; i++) {
+          auto id = [&](unsigned a, unsigned b, unsigned c) { return (int32_t)((i + a) + nn * ((j + b) + nn * (k + c))); };
+          for (int32_t v : {id(0, 0, 0), id(1, 0, 0), id(1, 1, 0), id(0, 1, 0), id(0, 0, 1), id(1, 0, 1), id(1, 1, 1), id(0, 1, 1)}) conn.push_back(v);
+        }
+    PerceptMesh eMesh(3u);
+    eMesh.set_unstructured_mesh(PMS_HEX8, N, conn.size() / 8, conn.data());
+    eMesh.add_coordinate_state_fields();
+    eMesh.set_field("coordinates_NM1", w.data());
+    eMesh.set_field("coordinates", x.data());
+    eMesh.set_field("coordinates_N", x.data());
+    ReferenceMeshSmootherConjugateGradientImpl<STKMesh> sm(&eMesh, NULL, NULL, 0, 1, 1e-3, 1);
+    sm.m_stage = 1;
+    sm.get_gradient();
+    double g = std::sqrt(eMesh.nodal_field_dot("cg_g", "cg_g"));
+    EXPECT_NEAR(g, 389575833.965, 1.0);
+    sm.m_stage = 0;
+    sm.get_gradient();
+    g = std::sqrt(eMesh.nodal_field_dot("cg_g", "cg_g"));
+    EXPECT_NEAR(g, 1.82363504678e-07, 1e-6);
+    bool valid = true;
+    size_t n_invalid = 0;
+    Double mtot = sm.total_metric(0.0, 1.0, valid, &n_invalid);
+    EXPECT_NEAR(mtot, 5.52566e-08, 1.e-7);
+    EXPECT_EQ(n_invalid, (size_t)391365);
+    EXPECT_EQ(ReferenceMeshSmootherConjugateGradientImpl<STKMesh>::parallel_count_invalid_elements(&eMesh), (size_t)391365);
+    std::printf("total_metric_and_gradient (STK hex8): mtot=%.6e n_invalid=%zu\n", (double)mtot, n_invalid);
+  }
   {  // TEST(heavy_perceptMeshSmoother, sgrid_perturbed_smooth), nele = 25, tol 1e-3, up to 1001 iterations/stage
     const unsigned nele = 25;
     PerceptMesh eMesh(3u);
