@@ -28,7 +28,7 @@
 #define PMS_RSQRT_CUBIC 1
 #endif
 #ifndef PMS_CORNER_ORDER
-#define PMS_CORNER_ORDER 1  // Gray code: 1.3 % faster element pass than the natural order (gpurun_out/ab_co.log)
+#define PMS_CORNER_ORDER 1  // Gray code: 1.3 % faster element pass than the natural order (profiles/r02_ab_corner_order.log)
 #endif
 #ifndef PMS_NO_OK_SELECT
 #define PMS_NO_OK_SELECT 1  // ShapeB1 gradient: no per-corner selects on detA > 0 (the element-level rule covers them)
@@ -357,7 +357,8 @@ PMS_DI void hex_metric_multi(const VC& vc, const VS& vs, const VO& vo, const dou
         const double detA = fma(al[k], fma(al[k], fma(al[k], d3, d2), d1), d0);
         const bool ok = detA > 0.0;
         const double P = cw * detA;
-        const double rr = fast_rsqrt(ok ? y * P * P : 1.0);
+        // (no select on the argument: y P^2 >= 0, and whatever inf/NaN a zero argument gives is dropped by the select below)
+        const double rr = fast_rsqrt(y * P * P);
         const double yr = y * rr;
         sum[k] += ok ? y * yr - detW : 0.0;
         if (!ok) invmask |= 1u << k;
@@ -407,7 +408,7 @@ PMS_DI double hex_shapeb1_metric_ilp(const double (&vc)[8][3], const double (&vo
     }
     y[c] = (ys[0] + ys[1]) + ys[2];
     const double P = FAC_3SQRT3 * fabs(dW[c]) * detA;
-    z[c] = ok[c] ? y[c] * P * P : 1.0;
+    z[c] = y[c] * P * P;  // >= 0; an invalid corner's inf/NaN is dropped by the select on ok[c] below
   }
   double r[8], hz[8];
 #pragma unroll
