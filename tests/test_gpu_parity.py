@@ -176,25 +176,36 @@ def test_blas1(kind):
     assert np.array_equal(g.download("cg_g"), g.download("cg_r"))
 
 
-@pytest.mark.parametrize("strict", [0, 1])
-def test_golden_perturbed_cube_100_on_gpu(strict):
-    """The reference's KAT (HeavyTestMeshSmoother.cpp:1352-1423) evaluated by the CUDA kernels.  Absolute
-    tolerances are the reference test's own (1.0, 1e-6, 1e-7).  The strict_fp build must also reproduce the
-    12 printed digits; the FMA build is held to 1e-9 (|g|_smooth is dominated by nearly degenerate corners,
-    where FMA contraction alone moves the 11th digit)."""
-    nele = 100
+GOLDEN = {  # HeavyTestMeshSmoother.cpp:1352-1358: nele -> (n_invalid, mtot, |g| untangle, |g| smooth)
+    100: (391365, 5.52566e-08, 1.82363504678e-07, 389575833.965),
+    200: (3189265, 7.08e-09, 1.63634415837e-08, 1124552264.63),
+    300: (10820052, 2.10961e-09, 3.97221589862e-09, 89552984978.3),
+}
+
+
+@pytest.mark.parametrize("kind,nele,strict", [("sgrid", 100, 0), ("sgrid", 100, 1), ("sgrid", 200, 0), ("sgrid", 300, 0),
+                                              ("hex8", 100, 0), ("hex8", 100, 1), ("hex8", 200, 0)])
+def test_golden_perturbed_cubes_on_gpu(kind, nele, strict):
+    """The reference's KAT (HeavyTestMeshSmoother.cpp:1352-1423; it runs the structured block and the STK hex8 mesh of the
+    same perturbed cube against the same numbers) evaluated by the CUDA kernels at nele = 100, 200, 300 (27 M cells: the
+    tile kernel's k chunks, seams, 64-bit strides and the unstructured CSR at bench-like sizes).  Absolute tolerances are
+    the reference test's own (1.0, 1e-6, 1e-7).  The strict_fp build must also reproduce the 12 printed digits; the FMA
+    build is held to 1e-9 (|g|_smooth is dominated by nearly degenerate corners, where FMA contraction alone moves the
+    11th digit)."""
+    n_inv, mtot, g_unt, g_smooth = GOLDEN[nele]
     X, W = meshes.perturbed_coords(nele, 1.0)
-    g = meshes.build(pb.api, "sgrid", nele, X, W, fixed=False, options={"strict_fp": strict})
+    g = meshes.build(pb.api, kind, nele, X, W, fixed=False, options={"strict_fp": strict})
     rtol = 1e-11 if strict else 1e-9
     g.get_gradient(1)
     gs = np.sqrt(g.dot("cg_g", "cg_g"))
-    assert abs(gs - 389575833.965) < 1.0 and abs(gs - 389575833.965) / 389575833.965 < rtol
+    assert abs(gs - g_smooth) < 1.0 * max(1.0, g_smooth / 389575833.965) and abs(gs - g_smooth) / g_smooth < rtol
     g.get_gradient(0)
     gu = np.sqrt(g.dot("cg_g", "cg_g"))
-    assert abs(gu - 1.82363504678e-07) < 1e-6 and abs(gu - 1.82363504678e-07) / 1.82363504678e-07 < rtol
+    assert abs(gu - g_unt) < 1e-6 and abs(gu - g_unt) / g_unt < rtol
     m, ninv = g.total_metric(0, 0.0)
-    assert abs(m - 5.52566e-08) < 1e-7 and abs(m - 5.52566e-08) / 5.52566e-08 < 1e-5
-    assert ninv == 391365
+    assert abs(m - mtot) < 1e-7 and abs(m - mtot) / mtot < 1e-5
+    assert ninv == n_inv
+    g.close()
 
 
 def test_csr_connectivity_bit_exact():
