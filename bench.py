@@ -286,6 +286,7 @@ def cg_iterations(E, ctx, stage, n_it=10):
         st.stage = stage
         st.num_invalid = ctx.count_invalid_elements()
         ninv0 = int(st.num_invalid)
+        st.untangled = 1 if ninv0 == 0 else 0  # run_algorithm: m_untangled = (m_num_invalid == 0), ReferenceMeshSmootherBase.cpp:262
         gm = ctx.run_one_iteration(st, 0.0)  # iteration 0 (edge lengths, first direction) is set-up: untimed
         ev0 = int(st.n_metric_evals)
         ctx.set_timing(1)
@@ -295,6 +296,8 @@ def cg_iterations(E, ctx, stage, n_it=10):
         for it in range(1, n_it + 1):
             st.iter = it
             st.num_invalid = ctx.count_invalid_elements()
+            if not st.untangled and st.num_invalid == 0:
+                st.untangled = 1  # ReferenceMeshSmootherBase.cpp:300
             gm = ctx.run_one_iteration(st, 0.0)
         barrier(E, ctx)
         dt = max_over_ranks(E, time.perf_counter() - t0)

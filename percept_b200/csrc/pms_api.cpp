@@ -17,6 +17,7 @@
 #include <fstream>
 #include <iomanip>
 #include <functional>
+#include <limits>
 #include <numeric>
 #include <thread>
 
@@ -298,7 +299,10 @@ void ensure_tetref(pms_ctx* c) {
 }
 
 // total_metric(alpha), Def.hpp:330-388, without materialising x + alpha*s
-void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t* ninv, bool count_eval = true) {
+// validity_suffices: the caller only needs the metric when no element is invalid (the line search on an untangled mesh
+// rejects such a trial whatever its value): a cached validity-only entry with invalid elements then answers with NaN.
+void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t* ninv, bool count_eval = true,
+                     bool validity_suffices = false) {
   (c->strict_fp ? pms_strict::set_variant : pms_fast::set_variant)(c->var_metric, c->var_grad, c->sgrid_fused ? 1 : 0);  // the switches live in the kernel TU: apply this ctx's
   DField& X = c->field("coordinates");
   DField& S = c->field("cg_s");
@@ -307,8 +311,8 @@ void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t
   if (c->cache_metric && !c->keep_elem) {
     for (auto& e : c->cache)
       if (e.xv == X.version && e.wv == W.version && e.stage == stage && e.alpha == alpha && e.use_ref == c->use_ref_mesh &&
-          (!with_s || e.sv == S.version)) {
-        *mtot = e.mtot;
+          (!with_s || e.sv == S.version) && (e.value_known || (validity_suffices && e.ninv > 0))) {
+        *mtot = e.value_known ? e.mtot : std::numeric_limits<double>::quiet_NaN();
         if (ninv) *ninv = e.ninv;
         return;
       }
@@ -334,6 +338,14 @@ void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t
   if (ninv) *ninv = n;
   (void)count_eval;
   if (c->cache_metric) {
+    for (auto& e : c->cache)  // a validity-only entry of this evaluation is completed, not duplicated
+      if (!e.value_known && e.xv == X.version && e.wv == W.version && e.sv == S.version && e.stage == stage && e.alpha == alpha &&
+          e.use_ref == c->use_ref_mesh) {
+        e.mtot = m;
+        e.ninv = n;
+        e.value_known = true;
+        return;
+      }
     if (c->cache.size() >= pms_ctx::CACHE_CAP) c->cache.erase(c->cache.begin());
     c->cache.push_back({X.version, S.version, W.version, stage, alpha, m, n, c->use_ref_mesh});
   }
@@ -341,15 +353,20 @@ void op_total_metric(pms_ctx* c, int stage, double alpha, double* mtot, uint64_t
 
 // total_metric at nb (8, 10, 12, 14 or 16) step lengths in one pass (hex meshes, one block).  Returns false when the kernel is
 // not available for this mesh / build; the caller then evaluates one alpha at a time.
-bool op_total_metric_multi(pms_ctx* c, int stage, int nb, const double* alphas, double* mtot, uint64_t* ninv) {
+// nf < nb (ShapeB1; rounded up to an even count >= 4): only the last nf step lengths get their metric, the first nb - nf only
+// their invalid-element count (mtot = NaN; cached as validity-only entries).  *nf_used returns what the kernel did.
+bool op_total_metric_multi(pms_ctx* c, int stage, int nb, const double* alphas, double* mtot, uint64_t* ninv, int nf = 0,
+                           int* nf_used = nullptr) {
   if (c->dev_blocks.size() != 1 || c->keep_elem || c->strict_fp || nb > pmsk::MULTI_ALPHA_NB) return false;
+  nf = (stage == 0 || nf <= 0 || nf >= nb) ? nb : std::max(4, (nf + 1) & ~1);  // kernels: every even count from 4
+  if (nf_used) *nf_used = nf;
   DField& X = c->field("coordinates");
   DField& S = c->field("cg_s");
   DField& W = c->field("coordinates_NM1");
   {
     Timed t(c, FAM_METRIC);
     (c->strict_fp ? pms_strict::set_variant : pms_fast::set_variant)(c->var_metric, c->var_grad, c->sgrid_fused ? 1 : 0);
-    if (!c->L->metric_multi(c->stream, c->dev_blocks[0], stage, c->use_ref_mesh ? 1 : 0, nb, X.d, S.d, W.d, c->Npad, alphas, c->R, 0,
+    if (!c->L->metric_multi(c->stream, c->dev_blocks[0], stage, c->use_ref_mesh ? 1 : 0, nb, nf, X.d, S.d, W.d, c->Npad, alphas, c->R, 0,
                             c->d_fixed)) {
       c->launches--;
       c->fam_launches[FAM_METRIC]--;
@@ -361,18 +378,26 @@ bool op_total_metric_multi(pms_ctx* c, int stage, int nb, const double* alphas, 
   double v[2 * pmsk::MULTI_ALPHA_NB];
   for (int k = 0; k < 2 * nb; k++) v[k] = c->h_out_d[k];
   for (int k = 0; k < nb; k++) {
-    mtot[k] = v[k];
+    mtot[k] = k < nb - nf ? std::numeric_limits<double>::quiet_NaN() : v[k];
     ninv[k] = (uint64_t)v[nb + k];
   }
   if (c->cache_metric)
     for (int k = 0; k < nb; k++) {
+      const bool known = k >= nb - nf;
       bool have = false;
       for (auto& e : c->cache)
-        have = have || (e.xv == X.version && e.wv == W.version && e.sv == S.version && e.stage == stage && e.alpha == alphas[k] &&
-                        e.use_ref == c->use_ref_mesh);
+        if (e.xv == X.version && e.wv == W.version && e.sv == S.version && e.stage == stage && e.alpha == alphas[k] &&
+            e.use_ref == c->use_ref_mesh) {
+          have = true;
+          if (!e.value_known && known) {
+            e.mtot = mtot[k];
+            e.ninv = ninv[k];
+            e.value_known = true;
+          }
+        }
       if (have) continue;
       if (c->cache.size() >= pms_ctx::CACHE_CAP) c->cache.erase(c->cache.begin());
-      c->cache.push_back({X.version, S.version, W.version, stage, alphas[k], mtot[k], ninv[k], c->use_ref_mesh});
+      c->cache.push_back({X.version, S.version, W.version, stage, alphas[k], mtot[k], ninv[k], c->use_ref_mesh, known});
     }
   return true;
 }
@@ -958,11 +983,12 @@ struct Driver {
   double gradNorm;
   Driver(pms_ctx* cc, pms_state* s, double gn) : c(cc), st(s), gradNorm(gn) {}
 
-  double tm(double alpha, bool& valid, uint64_t* ninv = nullptr) {
+  // validity_suffices: see op_total_metric (the Armijo loops on an untangled mesh: `converged && total_valid`)
+  double tm(double alpha, bool& valid, uint64_t* ninv = nullptr, bool validity_suffices = false) {
     double m;
     uint64_t n;
     const uint64_t before = c->fam_launches[FAM_METRIC];
-    op_total_metric(c, st->stage, alpha, &m, &n);
+    op_total_metric(c, st->stage, alpha, &m, &n, true, validity_suffices);
     if (c->fam_launches[FAM_METRIC] != before) st->n_metric_evals++;
     valid = (n == 0);
     if (ninv) *ninv = n;
@@ -977,7 +1003,9 @@ struct Driver {
     {
       const uint64_t xv = c->field("coordinates").version, sv = c->field("cg_s").version, wv = c->field("coordinates_NM1").version;
       for (auto& e : c->cache)
-        if (e.xv == xv && e.wv == wv && e.sv == sv && e.stage == st->stage && e.alpha == alpha && e.use_ref == c->use_ref_mesh) return;
+        if (e.xv == xv && e.wv == wv && e.sv == sv && e.stage == st->stage && e.alpha == alpha && e.use_ref == c->use_ref_mesh &&
+            (e.value_known || (st->untangled && e.ninv > 0)))
+          return;
     }
     // batch size from the previous line search: it visited spec_prev trials of the sequence (+1 for the quadratic
     // fit's a1); 8 when that is enough, else 12
@@ -993,7 +1021,19 @@ struct Driver {
       al[k] = a;
       a *= tau;  // the very multiplication the loop below performs, so the cache keys match bit for bit
     }
-    if (op_total_metric_multi(c, st->stage, nb, al, m, n)) st->n_metric_evals++;
+    // On an untangled mesh a trial with invalid elements is rejected whatever its metric, and the sequence starts with far
+    // too long steps: values are asked only from one trial before the previous batch's first all-valid one onwards, the
+    // earlier trials get their invalid count only (a wrong guess costs a single-alpha pass for the trial concerned).
+    int nf = nb;
+    if (st->stage == 1 && st->untangled && done == 0 && c->spec_kv_prev >= 0) nf = nb - std::max(0, c->spec_kv_prev - 1);
+    if (op_total_metric_multi(c, st->stage, nb, al, m, n, nf)) {
+      st->n_metric_evals++;
+      if (done == 0) {
+        int kv = 0;
+        while (kv < nb && n[kv] != 0) kv++;
+        c->spec_kv_prev = kv;
+      }
+    }
   }
   int spec_cur = 0;  // trials visited by the current line search (c->spec_prev: by the previous one)
 
@@ -1086,7 +1126,7 @@ struct Driver {
     while (!converged && liter < niter) {
       speculate(alpha, tau);
       spec_cur++;
-      metric = tm(alpha, total_valid, &n_invalid);
+      metric = tm(alpha, total_valid, &n_invalid, st->untangled != 0);
       const double mfac = alpha * armijo_offset_factor * mfac_mult;
       converged = (metric < metric_0 + mfac);
       if (st->untangled) converged = converged && total_valid;
@@ -1109,7 +1149,7 @@ struct Driver {
     while (!converged && liter < niter) {
       speculate(alpha, tau);
       spec_cur++;
-      metric = tm(alpha, total_valid);
+      metric = tm(alpha, total_valid, nullptr, st->untangled != 0);
       const double mfac = alpha * armijo_offset_factor * mfac_mult;
       converged = (metric < metric_0 + mfac);
       if (st->untangled) {
@@ -1819,6 +1859,8 @@ int pms_commit(pms_ctx* c) {
     m.csr_ent32 = c->d_csr_ent32;
     c->dev_blocks.push_back(m);
   }
+
+  if (!c->strict_fp && !c->dev_blocks.empty()) c->L->prepare_line_search_kernels(c->dev_blocks[0]);
 
   // reduction scratch: partial slots for the largest grid any kernel launches
   int nsm_dev = 148;

@@ -120,6 +120,7 @@ struct pms_ctx {
     double alpha, mtot;
     uint64_t ninv;
     bool use_ref;
+    bool value_known = true;  // false: only ninv is known (validity-only step length of a multi-alpha pass)
   };
   std::vector<CacheEnt> cache;
   static constexpr size_t CACHE_CAP = 32;
@@ -134,6 +135,7 @@ struct pms_ctx {
     double alpha0 = 0, sg = 0, ss = 0;
   } sinfo;
   int spec_prev = 0;  // trial step lengths the previous line search visited (sizes the next speculative batch)
+  int spec_kv_prev = -1;  // index of the first trial of the previous batch at which the whole mesh was valid (-1: unknown)
   bool speculate_line_search = true;  // evaluate the line search's alpha_init * tau^k trials in multi-alpha passes
   bool adj_fixed = false;
 

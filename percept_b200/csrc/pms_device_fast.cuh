@@ -298,7 +298,11 @@ PMS_DI double hex_metric_fast_v(const VC& vc, const VO& vo, bool& valid, double 
 // The 8 coefficients cost about two single evaluations of the corner; each further alpha costs ~20 FP64 instructions
 // (two Horner forms, one rsqrt) instead of ~94.  vs must already be zero at fixed nodes (update_coordinates.cpp:255).
 // sum[k] += metric of this element at al[k]; bit k of invmask set when any corner has det A(al[k]) <= 0.
-template <int STAGE, int NB, int CORNER_UNROLL = 8, class VC, class VS, class VO>
+// NF < NB: only the LAST NF step lengths get their metric; for the first NB - NF only det A(alpha) > 0 is tested (3 FMA +
+// a compare per corner instead of ~17 FP64) and their sums stay untouched.  The line search on an untangled mesh rejects a
+// trial with any invalid element whatever its metric, and its trial sequence runs from far too long steps down to the
+// accepted one, so the driver asks for values only near the previously accepted step (Driver::speculate).
+template <int STAGE, int NB, int CORNER_UNROLL = 8, int NF = NB, class VC, class VS, class VO>
 PMS_DI void hex_metric_multi(const VC& vc, const VS& vs, const VO& vo, const double (&al)[NB], double (&sum)[NB], unsigned& invmask) {
   invmask = 0;
   // CORNER_UNROLL < 8 keeps fewer corners' edge vectors and coefficients live (no spills), at the price of run-time
@@ -330,10 +334,11 @@ PMS_DI void hex_metric_multi(const VC& vc, const VS& vs, const VO& vo, const dou
 #pragma unroll
       for (int k = 0; k < NB; k++) {
         const double detA = fma(al[k], fma(al[k], fma(al[k], d3, d2), d1), d0);
+        if (!(detA > 0.0)) invmask |= 1u << k;
+        if (k < NB - NF) continue;
         const double vv = bw - detA;
         const double vp = vv > 0.0 ? vv : 0.0;
         sum[k] += vp * vp;
-        if (!(detA > 0.0)) invmask |= 1u << k;
       }
     } else {
       double C1[3], C2[3];
@@ -353,9 +358,13 @@ PMS_DI void hex_metric_multi(const VC& vc, const VS& vs, const VO& vo, const dou
       const double y1x2 = 2.0 * y1, cw = FAC_3SQRT3 * fabs(detW);
 #pragma unroll
       for (int k = 0; k < NB; k++) {
-        const double y = fma(al[k], fma(al[k], y2, y1x2), y0);
         const double detA = fma(al[k], fma(al[k], fma(al[k], d3, d2), d1), d0);
         const bool ok = detA > 0.0;
+        if (k < NB - NF) {  // validity only
+          if (!ok) invmask |= 1u << k;
+          continue;
+        }
+        const double y = fma(al[k], fma(al[k], y2, y1x2), y0);
         const double P = cw * detA;
         // (no select on the argument: y P^2 >= 0, and whatever inf/NaN a zero argument gives is dropped by the select below)
         const double rr = fast_rsqrt(y * P * P);

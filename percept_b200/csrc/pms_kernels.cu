@@ -1201,7 +1201,7 @@ template <int NB>
 struct AlphaPack {
   double a[NB];
 };
-template <int FL, int STAGE, int NB>
+template <int FL, int STAGE, int NB, int NF>
 __global__ void __launch_bounds__(NTP, MULTI_MINB) k_metric_multi(const MeshDev m, const double* __restrict__ x, const double* __restrict__ s,
                                                          const double* __restrict__ w, const long long stride,
                                                          const AlphaPack<NB> al, const Reduce R, const int slot) {
@@ -1253,7 +1253,7 @@ __global__ void __launch_bounds__(NTP, MULTI_MINB) k_metric_multi(const MeshDev 
     // equal either way and keeps the per-element array); ghost elements (multi-GPU aura) are not counted, so they are not evaluated either
     if (counted) {
       unsigned invmask;
-      hex_metric_multi<STAGE, NB, (NB >= 12 ? MULTI_CORNER_UNROLL_BIG : 8)>(VC, VS, VO, al.a, sums, invmask);
+      hex_metric_multi<STAGE, NB, (NB >= 12 ? MULTI_CORNER_UNROLL_BIG : 8), NF>(VC, VS, VO, al.a, sums, invmask);
 #pragma unroll
       for (int k = 0; k < NB; k++) cnt[k] += (invmask >> k) & 1u;
     }
@@ -1267,18 +1267,19 @@ __global__ void __launch_bounds__(NTP, MULTI_MINB) k_metric_multi(const MeshDev 
   grid_reduce<OpSum, 2 * NB, false>(v, 0ull, R, slot);
 }
 
-template <int FL, int STAGE, int NB>
+template <int FL, int STAGE, int NB, int NF>
 static void launch_metric_multi2(cudaStream_t st, const MeshDev& m, const double* x, const double* s, const double* w, long long stride,
                                  const double* alphas, const Reduce& R, int slot) {
   static_assert(2 * NB <= REDUCE_MAX_NV, "reduction scratch too small");
   const size_t smem = (size_t)72 * NTP * sizeof(double);
-  auto kern = k_metric_multi<FL, STAGE, NB>;
+  auto kern = k_metric_multi<FL, STAGE, NB, NF>;
   static int blocks_per_sm = 0;
   if (!blocks_per_sm) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NTP, smem);
     if (blocks_per_sm < 1) blocks_per_sm = 1;
   }
+  if (!x) return;  // prepare only (prepare_line_search_kernels): the attribute / occupancy calls have loaded the kernel
   AlphaPack<NB> al;
   for (int k = 0; k < NB; k++) al.a[k] = alphas[k];
   const long long nt = num_ptiles<FL>(m);
@@ -1286,37 +1287,54 @@ static void launch_metric_multi2(cudaStream_t st, const MeshDev& m, const double
   if (cap > R.max_blocks) cap = R.max_blocks;
   kern<<<(unsigned)(nt < cap ? (nt < 1 ? 1 : nt) : cap), NTP, smem, st>>>(m, x, s, w, stride, al, R, slot);
 }
+// nf = step lengths (the last ones of the batch) that get their metric: all of them in the untangle stage and on the
+// generic structured path (the tile kernel is the structured ShapeB1 path); the smallest even count >= nf from 4 in ShapeB1
+template <int FL, int NB, int NF>
+static void launch_metric_multi_nf(cudaStream_t st, const MeshDev& m, int nf, const double* x, const double* s, const double* w,
+                                   long long stride, const double* alphas, const Reduce& R, int slot) {
+  if constexpr (NF >= NB) {
+    launch_metric_multi2<FL, 1, NB, NB>(st, m, x, s, w, stride, alphas, R, slot);
+  } else {
+    if (nf <= NF)
+      launch_metric_multi2<FL, 1, NB, NF>(st, m, x, s, w, stride, alphas, R, slot);
+    else
+      launch_metric_multi_nf<FL, NB, NF + 2>(st, m, nf, x, s, w, stride, alphas, R, slot);
+  }
+}
 template <int FL, int NB>
-static void launch_metric_multi1(cudaStream_t st, const MeshDev& m, int stage, const double* x, const double* s, const double* w,
+static void launch_metric_multi1(cudaStream_t st, const MeshDev& m, int stage, int nf, const double* x, const double* s, const double* w,
                                  long long stride, const double* alphas, const Reduce& R, int slot) {
   if (stage == 0)
-    launch_metric_multi2<FL, 0, NB>(st, m, x, s, w, stride, alphas, R, slot);
+    launch_metric_multi2<FL, 0, NB, NB>(st, m, x, s, w, stride, alphas, R, slot);
+  else if (FL == FL_SGRID)
+    launch_metric_multi2<FL, 1, NB, NB>(st, m, x, s, w, stride, alphas, R, slot);
   else
-    launch_metric_multi2<FL, 1, NB>(st, m, x, s, w, stride, alphas, R, slot);
+    launch_metric_multi_nf<FL, NB, 4>(st, m, nf, x, s, w, stride, alphas, R, slot);
 }
-static bool launch_metric_multi(cudaStream_t st, const MeshDev& m, int stage, int use_ref, int nb, const double* x, const double* s,
+static bool launch_metric_multi(cudaStream_t st, const MeshDev& m, int stage, int use_ref, int nb, int nf, const double* x, const double* s,
                                 const double* w, long long stride, const double* alphas, const Reduce& R, int slot,
                                 const uint8_t* fixed) {
   if (STRICT || m.kind == KIND_TET4 || (stage != 0 && !use_ref) || (nb < 8 || nb > 16 || (nb & 1))) return false;  // kernels for 8, 10, 12, 14, 16
+  if (nf < 1 || nf > nb) nf = nb;
   // structured blocks: TMA-staged tile kernel (pms_sgrid_tile.cuh)
   // (ShapeB1 only: the cheap untangle polynomial runs faster in the per-thread pipelined kernel, 1.73 vs 1.97 ms)
-  if (m.kind == KIND_SGRID && stage == 1 && g_sgrid_tile && launch_sgrid_tile_multi(st, m, stage, nb, x, s, w, stride, fixed, alphas, R, slot))
+  if (m.kind == KIND_SGRID && stage == 1 && g_sgrid_tile && launch_sgrid_tile_multi(st, m, stage, nb, nf, x, s, w, stride, fixed, alphas, R, slot))
     return true;
   if (m.kind == KIND_SGRID) {
     switch (nb) {
-      case 8: launch_metric_multi1<FL_SGRID, 8>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
-      case 10: launch_metric_multi1<FL_SGRID, 10>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
-      case 12: launch_metric_multi1<FL_SGRID, 12>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
-      case 14: launch_metric_multi1<FL_SGRID, 14>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
-      default: launch_metric_multi1<FL_SGRID, 16>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+      case 8: launch_metric_multi1<FL_SGRID, 8>(st, m, stage, nf, x, s, w, stride, alphas, R, slot); break;
+      case 10: launch_metric_multi1<FL_SGRID, 10>(st, m, stage, nf, x, s, w, stride, alphas, R, slot); break;
+      case 12: launch_metric_multi1<FL_SGRID, 12>(st, m, stage, nf, x, s, w, stride, alphas, R, slot); break;
+      case 14: launch_metric_multi1<FL_SGRID, 14>(st, m, stage, nf, x, s, w, stride, alphas, R, slot); break;
+      default: launch_metric_multi1<FL_SGRID, 16>(st, m, stage, nf, x, s, w, stride, alphas, R, slot); break;
     }
   } else {
     switch (nb) {
-      case 8: launch_metric_multi1<FL_HEX8, 8>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
-      case 10: launch_metric_multi1<FL_HEX8, 10>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
-      case 12: launch_metric_multi1<FL_HEX8, 12>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
-      case 14: launch_metric_multi1<FL_HEX8, 14>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
-      default: launch_metric_multi1<FL_HEX8, 16>(st, m, stage, x, s, w, stride, alphas, R, slot); break;
+      case 8: launch_metric_multi1<FL_HEX8, 8>(st, m, stage, nf, x, s, w, stride, alphas, R, slot); break;
+      case 10: launch_metric_multi1<FL_HEX8, 10>(st, m, stage, nf, x, s, w, stride, alphas, R, slot); break;
+      case 12: launch_metric_multi1<FL_HEX8, 12>(st, m, stage, nf, x, s, w, stride, alphas, R, slot); break;
+      case 14: launch_metric_multi1<FL_HEX8, 14>(st, m, stage, nf, x, s, w, stride, alphas, R, slot); break;
+      default: launch_metric_multi1<FL_HEX8, 16>(st, m, stage, nf, x, s, w, stride, alphas, R, slot); break;
     }
   }
   return true;
@@ -2221,6 +2239,17 @@ __global__ void __launch_bounds__(NT) k_tet_ref(const MeshDev m, const double* _
 #pragma unroll
   for (int v = 0; v < 10; v++) out[(long long)v * out_stride + m.elem_off + e] = ref[v];
 }
+// CUDA loads a kernel when it is first used (lazy module loading, several ms for these large kernels), which would fall
+// into the first line searches of a run: touch every multi-alpha instantiation a mesh of this kind can ask for at commit.
+static void prepare_line_search_kernels(const MeshDev& m) {
+  if (STRICT || m.kind == KIND_TET4) return;
+  Reduce R{};
+  for (int stage = 0; stage < 2; stage++)
+    for (int nb = 8; nb <= 16; nb += 2)
+      for (int nf = 4; nf <= (stage == 0 ? 4 : nb); nf += 2)
+        launch_metric_multi(0, m, stage, 1, nb, nf, nullptr, nullptr, nullptr, 0, nullptr, R, 0, nullptr);
+}
+
 static void launch_tet_ref(cudaStream_t st, const MeshDev& m, const double* w, long long stride, double* out, long long out_stride) {
   if (m.kind == KIND_TET4 && m.nelems > 0)
     k_tet_ref<<<(unsigned)((m.nelems + NT - 1) / NT), NT, 0, st>>>(m, w, stride, out, out_stride);
@@ -2240,7 +2269,7 @@ static const Launchers g_launchers = {launch_metric,    launch_grad_elements, la
                                       launch_group_sum, launch_axpby,         launch_axpbypgz,    launch_set,
                                       launch_dot,       launch_cg_r_dots,     launch_cg_s_update, launch_cg_s_update_dots, launch_alpha0,
                                       launch_update,    launch_edge_lengths,  launch_divide,      launch_pack,
-                                      launch_unpack,    launch_elem_fixed_bits, launch_tet_ref, launch_grad_bricks, launch_elem_ws, elem_gather_grid, launch_shared_sum,
+                                      launch_unpack,    launch_elem_fixed_bits, launch_tet_ref, prepare_line_search_kernels, launch_grad_bricks, launch_elem_ws, elem_gather_grid, launch_shared_sum,
                                       launch_metric_multi, launch_refine_sgrid, launch_surf_project, launch_surf_snap, launch_surf_normals};
 
 const Launchers* launchers() { return &g_launchers; }

@@ -163,6 +163,8 @@ struct Launchers {
   void (*elem_fixed_bits)(cudaStream_t, const MeshDev&, const uint8_t* fixed, uint8_t* bits);
   // tet4: reference-mesh part of every element (W^-1, det W) from the reference coordinates w -> out[v*out_stride + e]
   void (*tet_ref)(cudaStream_t, const MeshDev&, const double* w, long long stride, double* out, long long out_stride);
+  // loads (CUDA lazy module loading) every multi-alpha kernel a mesh of this kind can ask for; no launch
+  void (*prepare_line_search_kernels)(const MeshDev&);
   // scratch-free hex8 gradient over bricks (default build only); returns false when unsupported
   bool (*grad_bricks)(cudaStream_t, const MeshDev&, const BrickDev&, int stage, const double* x, const double* w,
                       long long stride, const uint8_t* fixed, const uint8_t* node_owned, double* g, double* r_out,
@@ -177,10 +179,11 @@ struct Launchers {
   // cross-rank interface sum (structured block per GPU), ascending rank order
   void (*shared_sum)(cudaStream_t, long long nshared, const int32_t* nodes, const int64_t* ptr, const int64_t* ent_pos,
                      const int32_t* ent_cnt, const double* recvbuf, double* f, int ncomp, long long stride);
-  // hex metric at nb (8, 12 or 16) trial step lengths in one pass (line search speculation): out_d[slot + k] = metric at
-  // alphas[k], out_d[slot + nb + k] = number of invalid elements at alphas[k].  Returns false when not available
-  // (tet4, strict build, ShapeB1 without reference mesh).
-  bool (*metric_multi)(cudaStream_t, const MeshDev&, int stage, int use_ref, int nb, const double* x, const double* s,
+  // hex metric at nb (8, 10, 12, 14 or 16) trial step lengths in one pass (line search speculation): out_d[slot + k] = metric
+  // at alphas[k], out_d[slot + nb + k] = number of invalid elements at alphas[k].  nf < nb (ShapeB1 only; 4 or 6): only the
+  // LAST nf step lengths get their metric, the others only their invalid count (their out_d[slot + k] is meaningless).
+  // Returns false when not available (tet4, strict build, ShapeB1 without reference mesh).
+  bool (*metric_multi)(cudaStream_t, const MeshDev&, int stage, int use_ref, int nb, int nf, const double* x, const double* s,
                        const double* w, long long stride, const double* alphas, const Reduce&, int slot, const uint8_t* fixed);
   // StructuredGridRefiner: 2x prolongation of a 3-component nodal field of one block (coarse ni x nj x nk nodes at
   // src + src_off, component stride src_stride) onto the (2ni-1) x (2nj-1) x (2nk-1) block at dst + dst_off

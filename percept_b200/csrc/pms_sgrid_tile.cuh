@@ -416,7 +416,7 @@ struct TmVertsMasked {  // the search direction: zero at fixed nodes (bit p of f
   PMS_DI double operator()(int p, int r) const { return ((fx >> p) & 1u) ? 0.0 : v(p, r); }
 };
 
-template <int STAGE, int NB, bool WITH_S>
+template <int STAGE, int NB, bool WITH_S, int NF = NB>
 __global__ void __launch_bounds__(WS_NC + WS_NH, 1) k_sgrid_tile_metric(const MeshDev m, const double* __restrict__ x,
                                                                         const double* __restrict__ s, const double* __restrict__ w,
                                                                         const long long stride, const uint8_t* __restrict__ fixed,
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(WS_NC + WS_NH, 1) k_sgrid_tile_metric(const Me
 #pragma unroll
         for (int q = 0; q < NB; q++) es[q] = 0.0;
         unsigned invmask;
-        hex_metric_multi<STAGE, NB, TM_CORNER_UNROLL>(VC, VSM, VO, al.a, es, invmask);
+        hex_metric_multi<STAGE, NB, TM_CORNER_UNROLL, NF>(VC, VSM, VO, al.a, es, invmask);
 #pragma unroll
         for (int q = 0; q < NB; q++) {
           sums[q] += es[q];
@@ -681,10 +681,18 @@ static bool launch_grad_fused_sgrid(cudaStream_t st, const MeshDev& m, int stage
   return true;
 }
 
-template <int STAGE, int NB, bool WITH_S>
+template <int STAGE, int NB, bool WITH_S, int NF = NB>
 static bool launch_sgrid_tile_metric3(cudaStream_t st, const MeshDev& m, const double* x, const double* s, const double* w,
                                       long long stride, const uint8_t* fixed, const double* alphas, const Reduce& R, int slot,
                                       double* em, int32_t* ef) {
+  constexpr size_t smem = (size_t)(WS_NPL * TmPlane<WITH_S ? 3 : 2>::DOUBLES) * sizeof(double) + 2 * WS_NPL * 8;
+  auto kern = k_sgrid_tile_metric<STAGE, NB, WITH_S, NF>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  if (!x) return true;  // prepare only (prepare_line_search_kernels): the attribute call has loaded the kernel
   const int nci = m.ni - 1, ncj = m.nj - 1, nck = m.nk - 1;
   const int ntx = (nci + TL_X - 1) / TL_X, nty = (ncj + WS_TY - 1) / WS_TY;
   const long long ntiles = (long long)ntx * nty;
@@ -692,13 +700,6 @@ static bool launch_sgrid_tile_metric3(cudaStream_t st, const MeshDev& m, const d
   const int kc = tl_pick_chunk(ntiles, nck);
   const long long grid = ntiles * ((nck + kc - 1) / kc);
   if (grid > R.max_blocks || grid > 0x7fffffffLL) return false;
-  constexpr size_t smem = (size_t)(WS_NPL * TmPlane<WITH_S ? 3 : 2>::DOUBLES) * sizeof(double) + 2 * WS_NPL * 8;
-  auto kern = k_sgrid_tile_metric<STAGE, NB, WITH_S>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
   TileAlphas<NB> al;
   for (int q = 0; q < NB; q++) al.a[q] = alphas[q];
   kern<<<(unsigned)grid, WS_NC + WS_NH, smem, st>>>(m, x, s, w, stride, fixed, al, ntx, nty, kc, R, slot, em, ef);
@@ -723,20 +724,30 @@ static bool launch_sgrid_tile_metric(cudaStream_t st, const MeshDev& m, int stag
                 : launch_sgrid_tile_metric3<1, 1, false>(st, m, x, nullptr, w, stride, fixed, &alpha, R, slot, em, ef);
 }
 
+template <int NB, int NF>
+static bool launch_sgrid_tile_multi_nf(cudaStream_t st, const MeshDev& m, int nf, const double* x, const double* s, const double* w,
+                                       long long stride, const uint8_t* fixed, const double* alphas, const Reduce& R, int slot) {
+  if constexpr (NF >= NB) {
+    return launch_sgrid_tile_metric3<1, NB, true>(st, m, x, s, w, stride, fixed, alphas, R, slot, nullptr, nullptr);
+  } else {
+    if (nf <= NF) return launch_sgrid_tile_metric3<1, NB, true, NF>(st, m, x, s, w, stride, fixed, alphas, R, slot, nullptr, nullptr);
+    return launch_sgrid_tile_multi_nf<NB, NF + 2>(st, m, nf, x, s, w, stride, fixed, alphas, R, slot);
+  }
+}
 template <int NB>
-static bool launch_sgrid_tile_multi1(cudaStream_t st, const MeshDev& m, int stage, const double* x, const double* s, const double* w,
+static bool launch_sgrid_tile_multi1(cudaStream_t st, const MeshDev& m, int stage, int nf, const double* x, const double* s, const double* w,
                                      long long stride, const uint8_t* fixed, const double* alphas, const Reduce& R, int slot) {
   if (stage == 0) return launch_sgrid_tile_metric3<0, NB, true>(st, m, x, s, w, stride, fixed, alphas, R, slot, nullptr, nullptr);
-  return launch_sgrid_tile_metric3<1, NB, true>(st, m, x, s, w, stride, fixed, alphas, R, slot, nullptr, nullptr);
+  return launch_sgrid_tile_multi_nf<NB, 4>(st, m, nf, x, s, w, stride, fixed, alphas, R, slot);
 }
-static bool launch_sgrid_tile_multi(cudaStream_t st, const MeshDev& m, int stage, int nb, const double* x, const double* s,
+static bool launch_sgrid_tile_multi(cudaStream_t st, const MeshDev& m, int stage, int nb, int nf, const double* x, const double* s,
                                     const double* w, long long stride, const uint8_t* fixed, const double* alphas, const Reduce& R,
                                     int slot) {
-  if (STRICT || !s || !sgrid_tile_ok(m, x, s, w, stride, fixed)) return false;
-  if (nb == 8) return launch_sgrid_tile_multi1<8>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
-  if (nb == 10) return launch_sgrid_tile_multi1<10>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
-  if (nb == 12) return launch_sgrid_tile_multi1<12>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
-  if (nb == 14) return launch_sgrid_tile_multi1<14>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
-  if (nb == 16) return launch_sgrid_tile_multi1<16>(st, m, stage, x, s, w, stride, fixed, alphas, R, slot);
+  if (STRICT || (x && (!s || !sgrid_tile_ok(m, x, s, w, stride, fixed)))) return false;  // (x null: prepare only)
+  if (nb == 8) return launch_sgrid_tile_multi1<8>(st, m, stage, nf, x, s, w, stride, fixed, alphas, R, slot);
+  if (nb == 10) return launch_sgrid_tile_multi1<10>(st, m, stage, nf, x, s, w, stride, fixed, alphas, R, slot);
+  if (nb == 12) return launch_sgrid_tile_multi1<12>(st, m, stage, nf, x, s, w, stride, fixed, alphas, R, slot);
+  if (nb == 14) return launch_sgrid_tile_multi1<14>(st, m, stage, nf, x, s, w, stride, fixed, alphas, R, slot);
+  if (nb == 16) return launch_sgrid_tile_multi1<16>(st, m, stage, nf, x, s, w, stride, fixed, alphas, R, slot);
   return false;
 }
