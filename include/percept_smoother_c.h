@@ -71,7 +71,9 @@ const char* pms_last_error(const pms_ctx* ctx);
  *  "speculate_line_search"  default 1 (needs cache_metric 1, hex meshes, default build): the driver evaluates the
  *                  backtracking sequence alpha_init*tau^k in multi-alpha passes (pms_total_metric_multi), takes the
  *                  metric at the new coordinates from the fused metric+gradient pass and keeps that gradient for the
- *                  next iteration, and tests the quadratic step by moving there.  Same decisions and iteration
+ *                  next iteration, tests the quadratic step by moving there, and on an untangled mesh evaluates only the
+ *                  invalid-element count of the far-too-long leading trials (a trial with invalid elements is rejected
+ *                  whatever its metric).  Same decisions and iteration
  *                  counts; values agree to rounding (<= 1e-12) instead of bitwise.  Side effect: after
  *                  pms_run_one_iteration the field cg_g holds f'(x_new) (the gradient the next iteration starts
  *                  from) instead of f'(x_old).  0 = the reference's literal pass sequence.
