@@ -82,6 +82,9 @@ const char* pms_last_error(const pms_ctx* ctx);
  *  "variant_metric_corners" / "variant_grad_corners"  kernel variants (tuning aid)
  *  "sgrid_fused"   default 1: structured blocks use the one-pass tile kernels (TMA-staged node planes, in-CTA ordered
  *                  gather, pms_sgrid_tile.cuh); 0 = element pass + per-cell scratch + node gather.  Same bits either way.
+ *  "tet_ref_cache" default 1: tet4 kernels read W^-1 and det W of every element from a per-element cache that is rebuilt
+ *                  when coordinates_NM1 changes (10 coalesced values instead of gathering the 4 reference vertices in
+ *                  every pass); 0 = gather them.  Agrees to rounding.
  *  "elem_ws"       default 0: 1 = unstructured hex8 gradient in one kernel (node gather riding on the element loop,
  *                  pms_elem_ws.cuh); same bits as the two passes, measured slower (profiles/r02_elem_gather.md)         */
 int pms_set_option(pms_ctx* ctx, const char* key, double value);
