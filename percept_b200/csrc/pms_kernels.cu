@@ -1116,8 +1116,7 @@ template <int FL, int STAGE, bool WITH_S>
 __global__ void __launch_bounds__(NTP, OCC_MINB) k_metric_occ(const MeshDev m, const double* __restrict__ x, const double* __restrict__ s,
                                                               const double* __restrict__ w, const long long stride,
                                                               const double alpha, const Reduce R, const int slot) {
-  constexpr int NVAL = 8 * 3 * (WITH_S ? 3 : 2);
-  extern __shared__ double sm[];  // [NVAL][NTP]
+  extern __shared__ double sm[];  // [8 * 3 * (WITH_S ? 3 : 2)][NTP]
   const int tid = threadIdx.x;
   auto slot_in = [&](int arr, int a, int r) -> double* { return sm + ((arr * 8 + a) * 3 + r) * NTP + tid; };
   double val[1] = {0.0};
