@@ -178,3 +178,72 @@ def test_cached_tet_reference_matches_oracle_and_is_independent_of_the_current_m
         X = X + 0.02 / nele * np.sin(37.0 * X[::-1])
         for f in ("coordinates", "coordinates_N"):
             o.upload(f, X)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Validity-first line-search batches (Driver::speculate / op_total_metric in pms_api.cpp): on an untangled mesh a trial
+# with invalid elements is answered with (NaN, ninv) instead of its metric.  The reference's Armijo loops
+# (ReferenceMeshSmootherConjugateGradientDef.hpp:497-548) must take the same decisions either way.
+# ------------------------------------------------------------------------------------------------------------------
+def armijo_loops(trial, metric_0, alpha_init, offset_factor, untangled, dmax_relative, grad_norm, tau=0.5, niter=1000):
+    """The two back-tracking loops of line_search; trial(alpha) -> (metric, n_invalid).  -> (converged, alpha, visited)"""
+    alpha, visited, converged = alpha_init, [], False
+    liter = 0
+    while not converged and liter < niter:
+        metric, ninv = trial(alpha)
+        visited.append(alpha)
+        converged = metric < metric_0 + alpha * offset_factor
+        if untangled:
+            converged = converged and ninv == 0
+        if not converged:
+            alpha *= tau
+        if alpha < 1e-12 * alpha_init:
+            break
+        liter += 1
+    liter = 0
+    while not converged and liter < niter:  # (second loop, after the restart of the search direction)
+        metric, ninv = trial(alpha)
+        visited.append(alpha)
+        converged = metric < metric_0 + alpha * offset_factor
+        if untangled:
+            converged = converged and ninv == 0
+            if ninv == 0 and dmax_relative < grad_norm:
+                converged = True
+        if not converged:
+            alpha *= tau
+        if alpha < 1e-12 * alpha_init:
+            break
+        liter += 1
+    return converged, alpha, visited
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_validity_only_answers_leave_the_armijo_decisions_unchanged(seed):
+    rng = np.random.default_rng(seed)
+    metric_0 = 1.0
+    n_bad = int(rng.integers(0, 9))        # leading trials at which the mesh has invalid elements
+    n_reject = int(rng.integers(0, 8))     # valid trials that still fail the Armijo test
+    sometimes_lower = rng.random() < 0.5   # an invalid trial whose metric would pass the Armijo test on its own
+    table = {}
+
+    def full(alpha):
+        k = int(round(-np.log2(alpha)))
+        if k not in table:
+            if k < n_bad:
+                m = 0.5 if (sometimes_lower and k % 2 == 0) else 3.0 + rng.random()
+                table[k] = (m, int(rng.integers(1, 1000)))
+            elif k < n_bad + n_reject:
+                table[k] = (1.5 + rng.random(), 0)
+            else:
+                table[k] = (0.9, 0)
+        return table[k]
+
+    def validity_only(alpha):
+        m, ninv = full(alpha)
+        return (float("nan"), ninv) if ninv > 0 else (m, ninv)
+
+    args = (metric_0, 1.0, -1e-3, True, 1.0, 1e-6)
+    a = armijo_loops(full, *args)
+    b = armijo_loops(validity_only, *args)
+    assert a == b
+    assert a[0] and len(a[2]) == n_bad + n_reject + 1
